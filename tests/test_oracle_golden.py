@@ -1,0 +1,66 @@
+"""CPU: both oracle restatements reproduce the committed outputs of the reference BIT-exactly."""
+import numpy as np
+import pytest
+
+from golden_util import RECORD, golden_cases, load, unpack_adj
+from oracle import c_oracle, flock_numpy as fnp
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_numpy_port_matches_reference_golden(name):
+    g, m = load(name)
+    out = fnp.rollout(g["x0"], 200, comm_radius=m["comm_radius"], dt=m["dt"], centralized=m["centralized"],
+                      knn=m["knn"], record_every=1)
+    tr = out["traj"]
+    for t in RECORD:
+        assert np.array_equal(tr["x"][t - 1], g[f"x_{t}"])
+        assert np.array_equal(tr["u"][t - 1], g[f"u_{t}"])
+        assert np.array_equal(tr["values"][t - 1], g[f"values_{t}"])
+        assert np.array_equal(tr["adj"][t - 1], unpack_adj(g[f"adj_{t}"], m["n"]))
+    assert np.array_equal(out["rewards"], g["rewards"])
+    assert np.array_equal(out["adj_mean"], g["adj_mean_200"])
+    if m["knn"]:
+        assert np.array_equal(out["obs"], g["obs_200"])
+    st = fnp.get_stats(out["x"], out["r2"])
+    assert np.array_equal(st["vel_diffs"], g["stats_vel_diffs"])
+    assert np.array_equal(st["min_dists"], g["stats_min_dists"])
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_c_oracle_matches_reference_golden(name):
+    g, m = load(name)
+    kw = dict(comm_radius=m["comm_radius"], dt=m["dt"], centralized=m["centralized"])
+    prev = 0
+    x = g["x0"]
+    assert np.array_equal(c_oracle.helpers(x, m["comm_radius"])["values"], g["values_0"])
+    assert np.array_equal(c_oracle.controller(x, m["comm_radius"], m["centralized"]), g["u_0"])
+    rewards = []
+    for t in RECORD:
+        out = c_oracle.rollout(x, t - prev, knn=7 if m["knn"] else 0, **kw)
+        x, prev = out["x"], t
+        rewards.append(out["rewards"])
+        assert np.array_equal(x, g[f"x_{t}"])
+        assert np.array_equal(out["u"], g[f"u_{t}"])
+        assert np.array_equal(out["values"], g[f"values_{t}"])
+        assert np.array_equal((out["adj_mean"] > 0).astype(float), unpack_adj(g[f"adj_{t}"], m["n"]))
+        if m["knn"]:
+            assert np.array_equal(out["obs"], g[f"obs_{t}"])
+    assert np.array_equal(np.concatenate(rewards), g["rewards"])
+    assert np.array_equal(out["adj_mean"], g["adj_mean_200"])
+
+
+def test_smoke_seed0_golden():
+    """SURVEY.md section 4 smoke golden (reference reset() with np.random.seed(0) via the cfg path)."""
+    import os
+    from golden_util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "smoke_seed0.npz"))
+    assert g["x0"][0].tolist() == [0.1778536750997756, -1.0798168495725435, 8.174058699089354, 0.37089636162829187]
+    out = c_oracle.rollout(g["x0"], 200)
+    assert np.array_equal(out["x"], g["x_200"])
+    assert np.array_equal(out["rewards"], g["rewards"])
+    assert out["rewards"][0] == -15.534897470315922 and out["rewards"][-1] == -0.003264501952654671
+    assert np.array_equal(c_oracle.controller(g["x0"]), g["u_first"])
+    h = c_oracle.helpers(g["x0"])
+    assert np.array_equal(h["values"], g["values_0"]) and np.array_equal(h["adj_mean"], g["adj_mean_0"])
+    deg = (h["adj"].sum(1))
+    assert (deg.min(), deg.max()) == (2.0, 11.0) and abs(deg.mean() - 6.84) < 1e-12
