@@ -1,0 +1,401 @@
+// flock_abi.cu -- extern "C" boundary of libflock_b200.so (declared in include/flock_b200.h).
+// Host-side planning (how rows map to CTAs / lanes / shared memory) and kernel dispatch live here;
+// no torch or C++ types cross the ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <new>
+#include <utility>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/flock_b200.h"
+#include "flock_env_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(FLOCK_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));   \
+    } while (0)
+
+constexpr int kSMs = 148;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+inline unsigned align16(size_t v) { return (unsigned)((v + 15) & ~(size_t)15); }
+inline int round_up32(int v) { return (v + 31) & ~31; }
+
+struct Plan {
+    flock::KArgs k;
+    int lanes, threads, grid;
+    size_t smem;
+    bool exact, knn;
+};
+
+// Decide lanes-per-row, envs-per-CTA (or rows-per-tile) and the shared-memory layout.
+int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
+    if (!p) return fail(FLOCK_EINVAL, "params is NULL");
+    const int E = p->n_envs, N = p->n_agents;
+    if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
+    if ((long long)E * N > (1LL << 30)) return fail(FLOCK_EUNSUPPORTED, "E*N too large");
+    int row_lo = p->row_lo, row_hi = p->row_hi;
+    if (row_lo == 0 && row_hi == 0) row_hi = N;
+    if (row_lo < 0 || row_hi > N || row_lo >= row_hi) return fail(FLOCK_EINVAL, "bad row range [%d,%d)", row_lo, row_hi);
+    const int nrows = row_hi - row_lo;
+    pl.exact = (p->flags & FLOCK_EXACT_ORDER) != 0;
+    pl.knn = (p->flags & FLOCK_KNN_OBS) != 0;
+    if (pl.exact && tbytes != 8) return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER is an f64 mode");
+    if (pl.knn && p->knn != flock::KNN_K) return fail(FLOCK_EUNSUPPORTED, "knn=%d: only %d is built", p->knn, flock::KNN_K);
+
+    int lanes = p->lanes;
+    if (pl.exact) {
+        if (lanes > 1) return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER needs lanes = 1 (sequential j)");
+        lanes = 1;
+    } else if (lanes <= 0) {
+        lanes = 1;
+        const long long rows = (long long)E * nrows;
+        while (rows * lanes < (long long)kSMs * 1024 && lanes < 32 && lanes * 2 <= N) lanes *= 2;
+    } else if (lanes > 32 || (lanes & (lanes - 1))) {
+        return fail(FLOCK_EINVAL, "lanes=%d must be a power of two <= 32", lanes);
+    }
+
+    int G = 1, RT, tiles, threads;
+    if (nrows == N && N * lanes <= 512) {
+        // whole envs per CTA: maximise lane utilisation x balance of CTAs over the SMs
+        const int gmax = std::min(E, 512 / (N * lanes));
+        double best = -1.0;
+        for (int g = 1; g <= gmax; ++g) {
+            const int thr = round_up32(g * N * lanes);
+            const double util = (double)(g * N * lanes) / thr;
+            const int ctas = (E + g - 1) / g;
+            const double per_sm = (double)ctas / kSMs;
+            const double bal = per_sm >= 1.0 ? per_sm / (double)((ctas + kSMs - 1) / kSMs) : 1.0;
+            // prefer >= 128 threads per CTA when there is a choice (fewer CTA launches per SM)
+            const double score = util * bal * (thr >= 128 ? 1.0 : 0.9);
+            if (score > best + 1e-9) { best = score; G = g; }
+        }
+        RT = G * N; tiles = 1; threads = round_up32(RT * lanes);
+    } else {
+        if (nrows != N && E != 1 && false) return fail(FLOCK_EINVAL, "unreachable");
+        threads = 256;
+        RT = std::min(threads / lanes, nrows);
+        threads = round_up32(RT * lanes);
+        tiles = (nrows + RT - 1) / RT;
+    }
+    const int W = ((N + lanes - 1) / lanes + 31) / 32;
+    const size_t v4 = (size_t)4 * tbytes;
+    const bool centre = (tbytes == 4);
+    flock::KArgs &k = pl.k;
+    memset(&k, 0, sizeof(k));
+    k.off_xs = 0;
+    const size_t size_xs = (size_t)G * N * v4;
+    k.off_stage = k.off_masks = align16(size_xs);
+    const size_t size_stage = centre ? (size_t)G * N * 32 : 0;
+    const size_t size_masks = (size_t)RT * lanes * W * 4;
+    k.off_invdeg = align16(k.off_masks + std::max(size_stage, size_masks));
+    k.off_stats = align16(k.off_invdeg + (size_t)RT * tbytes);
+    pl.smem = (size_t)k.off_stats + (size_t)G * 2 * 8;
+    if (pl.smem > kMaxSmem)
+        return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
+                    N, pl.smem, kMaxSmem);
+    k.E = E; k.N = N; k.G = G; k.RT = RT; k.tiles = tiles; k.row_lo = row_lo; k.row_hi = row_hi;
+    k.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
+    {
+        // fast-path gradient mask as ONE compare r2 <= Rm.  Centralized: r2 <= R (flocking_relative.py:225).
+        // Decentralized (:205-206): additionally r2 < R2, i.e. r2 <= pred(R2) when R2 <= R.
+        const bool cen = k.centralized != 0;
+        const double R = p->comm_radius, R2 = p->comm_radius2;
+        const float Rf = (float)R, R2f = (float)R2;
+        k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
+        k.Rm_f = (cen || R2f > Rf) ? Rf : std::nextafterf(R2f, -1.0f);
+    }
+    k.W = W; k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
+    pl.lanes = lanes; pl.threads = threads;
+    pl.grid = ((E + G - 1) / G) * tiles;
+    return FLOCK_OK;
+}
+
+template <typename T, int LANES, bool EXACT, bool KNN>
+int launch_one(const Plan &pl, cudaStream_t st) {
+    auto kern = flock::flock_env_kernel<T, LANES, EXACT, KNN>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {   // opt in to > 48 KB dynamic shared memory once per (thread, device)
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        configured_dev = dev;
+    }
+    kern<<<pl.grid, pl.threads, pl.smem, st>>>(pl.k);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}
+
+template <typename T, bool KNN>
+int launch_lanes(const Plan &pl, cudaStream_t st) {
+    switch (pl.lanes) {
+        case 1: return launch_one<T, 1, false, KNN>(pl, st);
+        case 2: return launch_one<T, 2, false, KNN>(pl, st);
+        case 4: return launch_one<T, 4, false, KNN>(pl, st);
+        case 8: return launch_one<T, 8, false, KNN>(pl, st);
+        case 16: return launch_one<T, 16, false, KNN>(pl, st);
+        case 32: return launch_one<T, 32, false, KNN>(pl, st);
+    }
+    return fail(FLOCK_EINVAL, "lanes=%d", pl.lanes);
+}
+
+template <typename T>
+int launch(const Plan &pl, cudaStream_t st) {
+    if (pl.exact) {
+        if constexpr (std::is_same<T, double>::value)
+            return pl.knn ? launch_one<double, 1, true, true>(pl, st) : launch_one<double, 1, true, false>(pl, st);
+        else
+            return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER is an f64 mode");
+    }
+    return pl.knn ? launch_lanes<T, true>(pl, st) : launch_lanes<T, false>(pl, st);
+}
+
+bool misaligned(const void *p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); }
+
+template <typename T>
+int step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
+              T *reward, double *u_next, T *obs, void *stream) {
+    Plan pl;
+    int rc = make_plan(p, (int)sizeof(T), pl);
+    if (rc) return rc;
+    if (!x_in) return fail(FLOCK_EINVAL, "x_in is NULL");
+    if (x_out && x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
+    if (u_in && u_next == u_in) return fail(FLOCK_EINVAL, "u_next must not alias u_in");
+    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values) || misaligned(network) ||
+        misaligned(reward) || misaligned(u_next) || misaligned(obs))
+        return fail(FLOCK_EALIGN, "all device buffers must be 16-byte aligned");
+    if (pl.knn && !obs) pl.knn = false;
+    pl.k.x_in = x_in; pl.k.u_in = u_in; pl.k.x_out = x_out; pl.k.u_next = u_next;
+    pl.k.values = values; pl.k.network = network; pl.k.reward = reward; pl.k.obs = obs;
+    return launch<T>(pl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+template <typename T>
+int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, double *u_a, double *u_b, T *values,
+                 T *network, T *reward, T *rewards_all, T *obs, int32_t *final_in_b, void *stream) {
+    if (steps < 0) return fail(FLOCK_EINVAL, "steps=%d", steps);
+    if (!x_a || !x_b || !u_a || !u_b) return fail(FLOCK_EINVAL, "x_a/x_b/u_a/u_b must be non-NULL");
+    double *xi = x_a, *xo = x_b, *ui = u_a, *uo = u_b;
+    for (int t = 0; t < steps; ++t) {
+        T *r = rewards_all ? rewards_all + (size_t)t * p->n_envs : reward;
+        int rc = step_impl<T>(p, xi, ui, xo, values, network, r, uo, obs, stream);
+        if (rc) return rc;
+        std::swap(xi, xo);
+        std::swap(ui, uo);
+    }
+    if (rewards_all && reward && steps > 0)
+        CUDA_TRY(cudaMemcpyAsync(reward, rewards_all + (size_t)(steps - 1) * p->n_envs, sizeof(T) * p->n_envs,
+                                 cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+    if (final_in_b) *final_in_b = (steps & 1);
+    return FLOCK_OK;
+}
+
+}  // namespace
+
+// ---- host-buffer context -------------------------------------------------------------------------------
+struct FlockCtx {
+    FlockParams p;
+    int tbytes, device;
+    cudaStream_t stream;
+    double *x[2];      // ping-pong state; x[cur] is the current state
+    double *u[2];      // u[0]: action to apply (uploaded, or the cached controller action); u[1]: next
+    void *values, *network, *reward, *obs;
+    int cur;
+    int u_cached_flags;   // centralized flag the cached action was computed with; -1 = none
+};
+
+namespace {
+
+size_t n_x(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 4; }
+size_t n_u(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 2; }
+size_t n_val(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 6; }
+size_t n_net(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * c->p.n_agents; }
+size_t n_obs(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 4 * flock::KNN_K; }
+
+int ctx_run(FlockCtx *c, const double *u_dev, double *x_out, bool want_values, bool want_net, bool want_reward,
+            bool want_obs, double *u_next) {
+    void *obs = (want_obs && (c->p.flags & FLOCK_KNN_OBS)) ? c->obs : nullptr;
+    if (c->tbytes == 8)
+        return step_impl<double>(&c->p, c->x[c->cur], u_dev, x_out, want_values ? (double *)c->values : nullptr,
+                                 want_net ? (double *)c->network : nullptr, want_reward ? (double *)c->reward : nullptr,
+                                 u_next, (double *)obs, c->stream);
+    return step_impl<float>(&c->p, c->x[c->cur], u_dev, x_out, want_values ? (float *)c->values : nullptr,
+                            want_net ? (float *)c->network : nullptr, want_reward ? (float *)c->reward : nullptr, u_next,
+                            (float *)obs, c->stream);
+}
+
+int ctx_fetch(FlockCtx *c, void *values_host, void *network_host, void *reward_host, void *obs_host) {
+    const size_t tb = (size_t)c->tbytes;
+    if (values_host) CUDA_TRY(cudaMemcpyAsync(values_host, c->values, n_val(c) * tb, cudaMemcpyDeviceToHost, c->stream));
+    if (network_host) CUDA_TRY(cudaMemcpyAsync(network_host, c->network, n_net(c) * tb, cudaMemcpyDeviceToHost, c->stream));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, c->reward, (size_t)c->p.n_envs * tb, cudaMemcpyDeviceToHost, c->stream));
+    if (obs_host && (c->p.flags & FLOCK_KNN_OBS))
+        CUDA_TRY(cudaMemcpyAsync(obs_host, c->obs, n_obs(c) * tb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FLOCK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flock_abi_version(void) { return FLOCK_ABI_VERSION; }
+const char *flock_last_error(void) { return g_err.c_str(); }
+
+int flock_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
+                   double *network, double *reward, double *u_next, double *obs, void *stream) {
+    return step_impl<double>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, stream);
+}
+int flock_step_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, float *values,
+                   float *network, float *reward, double *u_next, float *obs, void *stream) {
+    return step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, stream);
+}
+int flock_rollout_f64(const FlockParams *p, int32_t steps, double *x_a, double *x_b, double *u_a, double *u_b,
+                      double *values, double *network, double *reward, double *rewards_all, double *obs,
+                      int32_t *final_in_b, void *stream) {
+    return rollout_impl<double>(p, steps, x_a, x_b, u_a, u_b, values, network, reward, rewards_all, obs, final_in_b, stream);
+}
+int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *x_b, double *u_a, double *u_b,
+                      float *values, float *network, float *reward, float *rewards_all, float *obs,
+                      int32_t *final_in_b, void *stream) {
+    return rollout_impl<float>(p, steps, x_a, x_b, u_a, u_b, values, network, reward, rewards_all, obs, final_in_b, stream);
+}
+
+void *flock_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void flock_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int flock_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int flock_ctx_create(FlockCtx **out, const FlockParams *p, int32_t dtype_bytes, int32_t device) {
+    if (!out || !p) return fail(FLOCK_EINVAL, "NULL argument");
+    if (dtype_bytes != 4 && dtype_bytes != 8) return fail(FLOCK_EINVAL, "dtype_bytes must be 4 or 8");
+    Plan pl;
+    int rc = make_plan(p, dtype_bytes, pl);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    FlockCtx *c = new (std::nothrow) FlockCtx();
+    if (!c) return fail(FLOCK_ENOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->p = *p; c->tbytes = dtype_bytes; c->device = device; c->cur = 0; c->u_cached_flags = -1;
+    const size_t tb = (size_t)dtype_bytes;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc((void **)&c->x[i], n_x(c) * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&c->u[i], n_u(c) * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->u[i], 0, n_u(c) * 8, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&c->values, n_val(c) * tb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->network, n_net(c) * tb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->reward, (size_t)p->n_envs * tb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->obs, n_obs(c) * tb);
+    if (e != cudaSuccess) {
+        flock_ctx_destroy(c);
+        return fail(e == cudaErrorMemoryAllocation ? FLOCK_ENOMEM : FLOCK_ECUDA, "ctx_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return FLOCK_OK;
+}
+
+void flock_ctx_destroy(FlockCtx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (int i = 0; i < 2; ++i) { cudaFree(c->x[i]); cudaFree(c->u[i]); }
+    cudaFree(c->values); cudaFree(c->network); cudaFree(c->reward); cudaFree(c->obs);
+    cudaGetLastError();
+    delete c;
+}
+
+int flock_ctx_set_params(FlockCtx *c, const FlockParams *p) {
+    if (!c || !p) return fail(FLOCK_EINVAL, "NULL argument");
+    if (p->n_envs != c->p.n_envs || p->n_agents != c->p.n_agents) return fail(FLOCK_EINVAL, "E and N are fixed per context");
+    Plan pl;
+    int rc = make_plan(p, c->tbytes, pl);
+    if (rc) return rc;
+    c->p = *p;
+    c->u_cached_flags = -1;
+    return FLOCK_OK;
+}
+
+int flock_ctx_set_state(FlockCtx *c, const double *x_host, void *values_host, void *network_host, void *reward_host,
+                        void *obs_host) {
+    if (!c || !x_host) return fail(FLOCK_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->x[c->cur], x_host, n_x(c) * 8, cudaMemcpyHostToDevice, c->stream));
+    int rc = ctx_run(c, nullptr, nullptr, values_host != nullptr, network_host != nullptr, reward_host != nullptr,
+                     obs_host != nullptr, c->u[0]);
+    if (rc) return rc;
+    c->u_cached_flags = c->p.flags & FLOCK_CENTRALIZED;
+    return ctx_fetch(c, values_host, network_host, reward_host, obs_host);
+}
+
+int flock_ctx_step(FlockCtx *c, const double *u_host, void *values_host, void *network_host, void *reward_host,
+                   void *obs_host) {
+    if (!c) return fail(FLOCK_EINVAL, "NULL context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (u_host) {
+        CUDA_TRY(cudaMemcpyAsync(c->u[0], u_host, n_u(c) * 8, cudaMemcpyHostToDevice, c->stream));
+    } else if (c->u_cached_flags != (c->p.flags & FLOCK_CENTRALIZED)) {
+        return fail(FLOCK_EINVAL, "no cached controller action for the current state / mode; call flock_ctx_controller or pass u");
+    }
+    int rc = ctx_run(c, c->u[0], c->x[c->cur ^ 1], values_host != nullptr, network_host != nullptr,
+                     reward_host != nullptr, obs_host != nullptr, c->u[1]);
+    if (rc) return rc;
+    c->cur ^= 1;
+    std::swap(c->u[0], c->u[1]);
+    c->u_cached_flags = c->p.flags & FLOCK_CENTRALIZED;
+    return ctx_fetch(c, values_host, network_host, reward_host, obs_host);
+}
+
+int flock_ctx_controller(FlockCtx *c, int32_t centralized, double *u_host) {
+    if (!c || !u_host) return fail(FLOCK_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int want = centralized ? FLOCK_CENTRALIZED : 0;
+    if (c->u_cached_flags != want) {
+        const int saved = c->p.flags;
+        c->p.flags = (saved & ~FLOCK_CENTRALIZED) | want;
+        int rc = ctx_run(c, nullptr, nullptr, false, false, false, false, c->u[0]);
+        c->p.flags = saved;
+        if (rc) return rc;
+        c->u_cached_flags = ((saved & FLOCK_CENTRALIZED) == want) ? want : -1;   // cache only the env's own mode
+    }
+    CUDA_TRY(cudaMemcpyAsync(u_host, c->u[0], n_u(c) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FLOCK_OK;
+}
+
+int flock_ctx_get_state(FlockCtx *c, double *x_host) {
+    if (!c || !x_host) return fail(FLOCK_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(x_host, c->x[c->cur], n_x(c) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FLOCK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""FlockVecEnv: E lockstep flocking envs on one GPU, PyTorch CUDA tensors in and out.
+
+torch is used for device memory and streams only; every numeric of the step is the hand-written
+kernel behind the C ABI (include/flock_b200.h: flock_step_*, flock_rollout_*), called through ctypes
+with raw device pointers on torch's current stream.  No CPU fallback: constructing one without a CUDA
+device, or without the built library, raises.
+
+Layout (all contiguous):
+  x[E,N,4] float64 (px,py,vx,vy) -- canonical state, double in every precision mode
+  u[E,N,2] float64 in [-1,1]
+  values[E,N,6], network[E,N,N], reward[E], obs[E,N,28]: float64 ('fp64', 'fp64-exact') or float32 ('fp32')
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PREC = {"fp64-exact": (torch.float64, True), "fp64": (torch.float64, False), "fp32": (torch.float32, False)}
+_IDS = {"FlockingRelative-v0": False, "Flocking-v0": True}
+
+
+class FlockVecEnv:
+    def __init__(self, env_id: str = "FlockingRelative-v0", num_envs: int = 1, n_agents: int = 100,
+                 precision: str = "fp32", device: str | int | torch.device = "cuda:0",
+                 comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
+                 adjacency_mode: str = "dense", max_episode_steps: int = 1000, lanes: int = 0,
+                 rows: tuple | None = None):
+        if env_id not in _IDS:
+            raise KeyError(f"unknown env id {env_id!r}; provided: {sorted(_IDS)}")
+        if precision not in _PREC:
+            raise ValueError(f"precision must be one of {sorted(_PREC)}")
+        if adjacency_mode not in ("dense", "none"):
+            raise ValueError("adjacency_mode must be 'dense' (reference layout) or 'none' (skip the [E,N,N] write)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("FlockVecEnv needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.E, self.N = int(num_envs), int(n_agents)
+        self.knn = _IDS[env_id]
+        self.env_id = env_id
+        self.precision = precision
+        self.dtype, self.exact = _PREC[precision]
+        self.centralized = bool(centralized)
+        self.comm_radius, self.dt = float(comm_radius), float(dt)
+        self.max_episode_steps = int(max_episode_steps)
+        self.adjacency_mode = adjacency_mode
+        self.rows = rows
+        self.lanes = int(lanes)
+        E, N, dev = self.E, self.N, self.device
+        f64 = torch.float64
+        self._x = [torch.zeros(E, N, 4, dtype=f64, device=dev) for _ in range(2)]
+        self._u = [torch.zeros(E, N, 2, dtype=f64, device=dev) for _ in range(2)]
+        self._cur = 0
+        self.values = torch.zeros(E, N, 6, dtype=self.dtype, device=dev)
+        self.network = torch.zeros(E, N, N, dtype=self.dtype, device=dev) if adjacency_mode == "dense" else None
+        self.reward = torch.zeros(E, dtype=self.dtype, device=dev)
+        self.obs = torch.zeros(E, N, 28, dtype=self.dtype, device=dev) if self.knn else None
+        self.elapsed = 0
+        self._fn_step = self.lib.flock_step_f64 if self.dtype == torch.float64 else self.lib.flock_step_f32
+        self._fn_roll = self.lib.flock_rollout_f64 if self.dtype == torch.float64 else self.lib.flock_rollout_f32
+        self._u_valid = False
+        self._refresh_params()
+
+    # ---- plumbing ----------------------------------------------------------------------------------------
+    def _refresh_params(self):
+        self._params = _lib.make_params(self.E, self.N, comm_radius=self.comm_radius, dt=self.dt,
+                                        centralized=self.centralized, exact=self.exact, knn_obs=self.knn,
+                                        rows=self.rows, lanes=self.lanes)
+        self._pp = ctypes.byref(self._params)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def x(self) -> torch.Tensor:
+        return self._x[self._cur]
+
+    @property
+    def u_cached(self) -> torch.Tensor:
+        """controller() action for the current state (valid after reset/step)."""
+        return self._u[self._cur]
+
+    def _observation(self):
+        return (self.obs if self.knn else self.values), self.network
+
+    def _launch(self, x_in, u_in, x_out, u_next, want_obs=True):
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn_step(self._pp, self._ptr(x_in), self._ptr(u_in), self._ptr(x_out),
+                                     self._ptr(self.values) if want_obs else None,
+                                     self._ptr(self.network) if want_obs else None,
+                                     self._ptr(self.reward) if want_obs else None,
+                                     self._ptr(u_next), self._ptr(self.obs) if want_obs else None,
+                                     self._stream()))
+
+    # ---- API -----------------------------------------------------------------------------------------------
+    def reset(self, x0=None, seed: int | None = None):
+        """Inject initial states (x0[E,N,4], torch or NumPy; default: the synthetic cfg law, seed per env) and
+        run the pair pass on them.  Returns (values|obs, network)."""
+        if x0 is None:
+            from .synthetic import DEFAULT_SEED, initial_states_fast
+            x0 = initial_states_fast(self.E, self.N, DEFAULT_SEED if seed is None else seed)
+        x0 = torch.as_tensor(np.asarray(x0) if not torch.is_tensor(x0) else x0, dtype=torch.float64)
+        self._x[self._cur].copy_(x0.reshape(self.E, self.N, 4), non_blocking=True)
+        self._launch(self.x, None, None, self._u[self._cur])
+        self._u_valid = True
+        self.elapsed = 0
+        return self._observation()
+
+    def set_state(self, x0):
+        return self.reset(x0)
+
+    def get_state(self) -> torch.Tensor:
+        return self.x.clone()
+
+    def controller(self, centralized: bool | None = None) -> torch.Tensor:
+        """flocking_relative.py:194-212 for every env: u[E,N,2] float64 (a view of the cached action)."""
+        cen = self.centralized if centralized is None else bool(centralized)
+        if cen == self.centralized and self._u_valid:
+            return self.u_cached
+        saved = self.centralized
+        self.centralized = cen
+        self._refresh_params()
+        out = torch.empty_like(self.u_cached) if cen != saved else self._u[self._cur]
+        self._launch(self.x, None, None, out, want_obs=False)
+        self.centralized = saved
+        self._refresh_params()
+        if cen == saved:
+            self._u_valid = True
+        return out
+
+    def step(self, u: torch.Tensor | None = None):
+        """One lockstep env step.  u[E,N,2] (any float dtype, on the device) or None = apply controller().
+        Returns ((values|obs, network), reward[E], done[E] bool, {})."""
+        if u is None:
+            u_in = self.controller()
+        else:
+            u_in = u.to(device=self.device, dtype=torch.float64).reshape(self.E, self.N, 2).contiguous()
+        nxt = self._cur ^ 1
+        u_next = self._u[nxt]
+        if u_in.data_ptr() == u_next.data_ptr():     # caller handed us our own buffer back
+            u_in = u_in.clone()
+        self._launch(self.x, u_in, self._x[nxt], u_next)
+        self._cur = nxt
+        self._u_valid = True
+        self.elapsed += 1
+        done = torch.full((self.E,), self.elapsed >= self.max_episode_steps, dtype=torch.bool, device=self.device)
+        return self._observation(), self.reward, done, {}
+
+    def rollout(self, steps: int, rewards_out: torch.Tensor | None = None):
+        """`steps` x {u = controller(); step(u)} launched back to back from C (no per-step Python).
+        Observation tensors hold the last step; rewards_out[steps,E] (optional) gets every step's reward."""
+        if not self._u_valid:
+            self.controller()
+        a, b = self._cur, self._cur ^ 1
+        fin = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn_roll(self._pp, int(steps), self._ptr(self._x[a]), self._ptr(self._x[b]),
+                                     self._ptr(self._u[a]), self._ptr(self._u[b]), self._ptr(self.values),
+                                     self._ptr(self.network), self._ptr(self.reward), self._ptr(rewards_out),
+                                     self._ptr(self.obs), ctypes.byref(fin), self._stream()))
+        self._cur = b if fin.value else a
+        self.elapsed += int(steps)
+        return self._observation(), self.reward
+
+    def close(self):
+        pass

@@ -1,0 +1,131 @@
+/* flock_b200.h -- C ABI of libflock_b200.so: gym-flock's flocking step on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of katetolstaya/gym-flock: the per-step update
+ * of FlockingRelativeEnv / FlockingEnv.  Reference citations (file:line) are relative to
+ * gym_flock/envs/flocking/ of the reference tree.
+ *
+ *   what the reference does per step                         where
+ *   -------------------------------------------------------  ------------------------------
+ *   step(u): Euler integration of x[N,4] with u*10           flocking_relative.py:91-105
+ *   compute_helpers(): diff, r2, adjacency, 6 features        flocking_relative.py:111-134
+ *   instant_cost(): -(var vx + var vy)                        flocking_relative.py:145-147
+ *   controller(): Tanner potential gradient + alignment       flocking_relative.py:194-226
+ *   get_observation(): 7-nearest-neighbour state differences  flocking.py:20-24
+ *
+ * The reference is Python/NumPy and has no FFI; the "binding" a maintainer adds is a ctypes stub
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - State-side arrays are ALWAYS double: x[E][N][4] = (px,py,vx,vy), u[E][N][2] in [-1,1].
+ *   - Observation-side arrays (values, network, reward, obs) are double for *_f64 and float for *_f32.
+ *   - All device buffers are caller-owned, contiguous, 16-byte aligned.  The library allocates nothing
+ *     behind device-pointer entry points; they are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), re-entrant, and never synchronise.
+ *   - Every entry point returns 0 on success or a negative FLOCK_E* code; it never throws or exits.
+ *     flock_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef FLOCK_B200_H
+#define FLOCK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOCK_ABI_VERSION 1
+
+/* flags */
+#define FLOCK_CENTRALIZED   0x1   /* controller(centralized=True), flocking_relative.py:200-206 */
+#define FLOCK_EXACT_ORDER   0x2   /* f64 only: sequential-j, unfused IEEE arithmetic == NumPy bit for bit */
+#define FLOCK_KNN_OBS       0x4   /* also write Flocking-v0's obs[N][4*knn] (flocking.py:20-24) */
+
+/* error codes */
+#define FLOCK_OK             0
+#define FLOCK_EINVAL        -1   /* bad shape / flag / null pointer */
+#define FLOCK_EALIGN        -2   /* pointer not 16-byte aligned */
+#define FLOCK_EUNSUPPORTED  -3   /* size outside what the selected mode supports */
+#define FLOCK_ECUDA         -4   /* CUDA runtime error (message in flock_last_error) */
+#define FLOCK_ENOMEM        -5
+
+typedef struct FlockParams {
+    int32_t n_envs;         /* E: independent environments stepped in lockstep */
+    int32_t n_agents;       /* N  (self.n_agents, flocking_relative.py:38) */
+    double  comm_radius;    /* R  (:39) -- the UNSQUARED radius masks the potential gradient (:225) */
+    double  comm_radius2;   /* R*R (:44) -- adjacency threshold, strict < (:117) */
+    double  dt;             /* (:40) */
+    double  action_scalar;  /* 10.0 (:64) */
+    int32_t flags;          /* FLOCK_* */
+    int32_t knn;            /* neighbours in obs; 7 (flocking.py:9); only with FLOCK_KNN_OBS */
+    int32_t row_lo;         /* swarm sharding: this call computes rows [row_lo,row_hi) of every env; */
+    int32_t row_hi;         /*   0,0 (or 0,N) = all rows.  x_in / u_in are always full [E][N][*]. */
+    int32_t lanes;          /* threads cooperating on one row (power of two <= 32); 0 = choose */
+    int32_t reserved;
+} FlockParams;
+
+int         flock_abi_version(void);
+const char *flock_last_error(void);
+int         flock_device_count(void);
+/* page-locked host memory for the host-buffer API (so NumPy-side bindings can get full PCIe rate) */
+void       *flock_host_alloc(size_t bytes);
+void        flock_host_free(void *p);
+
+/* One fused step on device buffers.
+ *   x' = u_in ? integrate(x_in, u_in) : x_in          (flocking_relative.py:96-105)
+ *   x_out (if non-NULL) <- x'   (all rows of every env; x_out may NOT alias x_in)
+ *   then ONE pass over the ordered pairs of x' produces, for rows [row_lo,row_hi):
+ *     values [E][N][6]      state_values   (:124-129)           (nullable)
+ *     network[E][N][N]      adj_mat_mean   (:117-122,131-132)   (nullable: skip the dense write)
+ *     reward [E]            instant_cost   (:145-147)           (nullable)
+ *     u_next [E][N][2]      controller() on x', double          (nullable)
+ *     obs    [E][N][4*knn]  FlockingEnv.get_observation()       (FLOCK_KNN_OBS; nullable)
+ * Replaces: FlockingRelativeEnv.step + compute_helpers + instant_cost + the following controller().
+ */
+int flock_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out,
+                   double *values, double *network, double *reward, double *u_next, double *obs,
+                   void *stream);
+int flock_step_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out,
+                   float *values, float *network, float *reward, double *u_next, float *obs,
+                   void *stream);
+
+/* `steps` fused steps with the internal controller (the driver loop {u=controller(); step(u)}),
+ * launched back to back on `stream` from C (no per-step host round trip).
+ *   x_a / x_b: ping-pong state buffers, x_a holds the start state; returns in *final_in_b whether the
+ *              final state is in x_b (1) or x_a (0).   u_a / u_b: ping-pong actions; u_a must hold
+ *              controller(x_a) on entry (as produced by a previous flock_step_* call's u_next).
+ *   Observation-side outputs are overwritten every step (they hold the last step on return);
+ *   rewards_all (nullable) is [steps][E] and receives every step's reward.
+ */
+int flock_rollout_f64(const FlockParams *p, int32_t steps, double *x_a, double *x_b, double *u_a, double *u_b,
+                      double *values, double *network, double *reward, double *rewards_all, double *obs,
+                      int32_t *final_in_b, void *stream);
+int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *x_b, double *u_a, double *u_b,
+                      float *values, float *network, float *reward, float *rewards_all, float *obs,
+                      int32_t *final_in_b, void *stream);
+
+/* ---- host-buffer context API (what a NumPy-only binding uses; no torch needed) ----------------
+ * A context owns device buffers + pinned staging for (E, N); calls take HOST pointers, copy in,
+ * launch, copy out and synchronise before returning.  dtype_bytes = 8 (f64) or 4 (f32).
+ */
+typedef struct FlockCtx FlockCtx;
+
+int  flock_ctx_create(FlockCtx **out, const FlockParams *p, int32_t dtype_bytes, int32_t device);
+void flock_ctx_destroy(FlockCtx *ctx);
+int  flock_ctx_set_params(FlockCtx *ctx, const FlockParams *p);          /* E, N must not change */
+/* x <- host state [E][N][4]; runs the pair pass on it (no integration): the reference's
+ * `self.x = x0; self.compute_helpers()`.  Outputs nullable; observation-side outputs have the
+ * context's dtype. */
+int  flock_ctx_set_state(FlockCtx *ctx, const double *x_host,
+                         void *values_host, void *network_host, void *reward_host, void *obs_host);
+/* step(u): u_host [E][N][2] (NULL = use the cached controller action).  Outputs nullable. */
+int  flock_ctx_step(FlockCtx *ctx, const double *u_host,
+                    void *values_host, void *network_host, void *reward_host, void *obs_host);
+/* controller(centralized): copies the controller action for the CURRENT state to u_host [E][N][2]. */
+int  flock_ctx_controller(FlockCtx *ctx, int32_t centralized, double *u_host);
+int  flock_ctx_get_state(FlockCtx *ctx, double *x_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOCK_B200_H */

@@ -1,0 +1,99 @@
+"""CPU: the C-ABI library loads, exports every symbol include/flock_b200.h declares, and rejects bad
+arguments without touching a GPU.  (No compute calls here.)"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from gym_flock_b200 import _lib
+    if _lib.needs_build():
+        _lib.build()
+    return _lib.lib()
+
+
+def test_every_declared_symbol_is_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "flock_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(flock_[a-z0-9_]+)\s*\(", hdr))
+    assert {"flock_step_f64", "flock_step_f32", "flock_rollout_f64", "flock_rollout_f32", "flock_ctx_create",
+            "flock_ctx_step", "flock_ctx_controller", "flock_last_error"} <= names
+    for n in sorted(names):
+        assert hasattr(L, n), n
+    assert L.flock_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header():
+    from gym_flock_b200._lib import FlockParams
+    assert ctypes.sizeof(FlockParams) == 64
+    assert FlockParams.comm_radius.offset == 8 and FlockParams.flags.offset == 40 and FlockParams.lanes.offset == 56
+
+
+def test_argument_validation_needs_no_gpu(L):
+    from gym_flock_b200 import _lib
+    buf = np.zeros(64, dtype=np.float64)
+    ptr = ctypes.c_void_p((buf.ctypes.data + 15) & ~15)
+
+    def call(p, x=ptr, xo=None):
+        return L.flock_step_f64(ctypes.byref(p), x, None, xo, None, None, None, None, None, None)
+
+    assert call(_lib.make_params(0, 4)) == -1                      # FLOCK_EINVAL: E < 1
+    assert b"n_envs" in L.flock_last_error()
+    assert call(_lib.make_params(1, 4, lanes=3)) == -1             # lanes not a power of two
+    assert call(_lib.make_params(1, 4, exact=True, lanes=4)) == -1  # exact needs sequential j
+    assert call(_lib.make_params(1, 4, rows=(3, 2))) == -1
+    assert call(_lib.make_params(1, 100000)) == -3                 # FLOCK_EUNSUPPORTED: beyond resident smem
+    assert call(_lib.make_params(1, 4), x=None) == -1
+    assert call(_lib.make_params(1, 4), xo=ptr) == -1              # x_out aliases x_in
+    assert call(_lib.make_params(1, 4), x=ctypes.c_void_p(ptr.value + 8)) == -2   # FLOCK_EALIGN
+    p32 = _lib.make_params(1, 4, exact=True)
+    assert L.flock_step_f32(ctypes.byref(p32), ptr, None, None, None, None, None, None, None, None) == -1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    import gym_flock_b200 as gf
+    with pytest.raises(RuntimeError):
+        gf.HostFlockBatch(1, 10)
+    with pytest.raises(RuntimeError):
+        gf.FlockVecEnv(num_envs=1, n_agents=10)
+    env = gf.FlockingRelativeEnv()
+    env.n_agents = 4
+    with pytest.raises(RuntimeError):
+        env.set_state(np.zeros((4, 4)))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gym_flock_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "gym_flock_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("__oracle_stub__", ""), os.path.join(dirpath, f)
+
+
+def test_drop_in_surface_and_synthetic_states():
+    import gym_flock_b200 as gf
+    from gym_flock_b200.synthetic import initial_state, initial_states
+    env = gf.FlockingRelativeEnv()
+    for attr, val in dict(n_agents=100, comm_radius=0.9, dt=0.01, v_max=5.0, r_max=1.0, action_scalar=10.0,
+                          nx_system=4, n_features=6, nu=2, mean_pooling=True, centralized=True).items():
+        assert getattr(env, attr) == val
+    assert abs(env.comm_radius2 - 0.81) < 1e-15 and isinstance(env.seed(5), list)
+    assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0"}
+    with pytest.raises(KeyError):
+        gf.make("Shepherding-v0")
+    a, b = initial_state(50, seed=7, min_dist=0.1), initial_states(2, 50, seed=7, min_dist=0.1)
+    assert np.array_equal(a, b[0]) and not np.array_equal(b[0], b[1])
+    d = a[:, None, :2] - a[None, :, :2]
+    r2 = (d ** 2).sum(-1) + np.eye(50) * 9
+    assert r2.min() >= 0.01

@@ -1,0 +1,135 @@
+"""GPU: the drop-in gym API (make/reset/step/controller/...) behaves like the reference classes."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg(dict):
+    def getfloat(self, k): return float(self[k])
+    def getint(self, k): return int(self[k])
+
+
+def test_make_reset_rollout_matches_smoke_golden():
+    """SURVEY.md section 4 smoke: params_from_cfg + np.random.seed(0) + reset() + 200 x {controller, step}."""
+    import gym_flock_b200 as gf
+    g = np.load(os.path.join(GOLDEN_DIR, "smoke_seed0.npz"))
+    env = gf.make('FlockingRelative-v0')
+    env.env.params_from_cfg(Cfg(comm_radius=0.9, n_agents=100, v_max=5.0, dt=0.01))
+    assert env.env.r_max == g["r_max"]
+    np.random.seed(0)
+    values0, net0 = env.reset()
+    assert np.allclose(env.env.x, g["x0"], rtol=0, atol=1e-12)      # libm cos/sin may differ in the last ulp
+    env.env.set_state(g["x0"])                                       # continue from the committed BYTES
+    assert np.array_equal(env.env.state_values, g["values_0"]) and np.array_equal(env.env.state_network, g["adj_mean_0"])
+    rewards = []
+    for t in range(200):
+        u = env.env.controller()
+        if t == 0:
+            assert np.array_equal(u, g["u_first"])
+        (values, net), r, done, info = env.step(u)
+        assert done is False and info == {} and isinstance(r, float)
+        assert values.shape == (100, 6) and net.shape == (100, 100) and values.dtype == np.float64
+        rewards.append(r)
+    assert np.array_equal(np.array(rewards), g["rewards"])
+    assert np.array_equal(env.env.x, g["x_200"])
+    st = env.env.get_stats()
+    assert np.array_equal(st["vel_diffs"], g["stats_vel_diffs"]) and np.array_equal(st["min_dists"], g["stats_min_dists"])
+    env.close()
+
+
+def test_flocking_v0_observation_and_errors():
+    import gym_flock_b200 as gf
+    g = np.load(os.path.join(GOLDEN_DIR, "flk_n8_cen.npz"))
+    env = gf.FlockingEnv()
+    assert env.n_neighbors == 7 and env.n_f == 28 and env.nx_system == 4 and env.n_features == 6 and env.nu == 2
+    assert env.action_space.shape == (200,) and env.observation_space.shape == (100, 6)
+    env.n_agents = 8
+    obs, net = env.set_state(g["x0"])
+    assert obs.shape == (8, 28) and net.shape == (8, 8)
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(16))                     # flocking_relative.py:94: only (N, 2) is accepted
+    with pytest.raises(AssertionError):
+        env.step(np.zeros((1, 8, 2)))
+    for t in range(1, 3):
+        (obs, net), r, done, info = env.step(env.controller())
+        assert np.array_equal(obs, g[f"obs_{t}"])
+    # state injection by attribute, the reference idiom
+    env.x = g["x_50"]
+    env.compute_helpers()
+    assert np.array_equal(env.state_values, g["values_50"])
+    # in-place edits of env.x are picked up as well
+    env.x[:] = g["x_100"]
+    assert np.array_equal(env.controller(), np.array(env.controller(centralized=True)))
+    (obs, net), r, _, _ = env.step(env.controller())
+    env.n_agents = 5
+    env.x = g["x0"][:5]
+    env.compute_helpers()
+    with pytest.raises(IndexError):
+        env.get_observation()                      # flocking.py:23-24 raises for N < 7
+    env.close()
+
+
+def test_decentralized_controller_and_float32_actions():
+    import gym_flock_b200 as gf
+    g = np.load(os.path.join(GOLDEN_DIR, "rel_n100_dec.npz"))
+    env = gf.FlockingRelativeEnv()
+    env.set_state(g["x0"])
+    assert np.array_equal(env.controller(centralized=False), g["u_0"])
+    u = env.controller(centralized=False)
+    (v, n), r, _, _ = env.step(u.astype(np.float32).astype(np.float64))   # promoted actions keep state float64
+    assert env.x.dtype == np.float64
+    env.close()
+
+
+def test_time_limit_and_reset_escape():
+    import gym_flock_b200 as gf
+    env = gf.make('Flocking-v0')
+    assert env._max_episode_steps == 1000
+    env.env.reset_max_tries = 50
+    with pytest.raises(RuntimeError):
+        env.reset()                                 # constructor defaults never admit a configuration
+    env.env.params_from_cfg(Cfg(comm_radius=0.9, n_agents=20, v_max=5.0, dt=0.01))
+    env.env.reset_max_tries = 20000
+    np.random.seed(3)
+    obs, net = env.reset()
+    assert obs.shape == (20, 28)
+    env._max_episode_steps = 3
+    dones = [env.step(env.controller())[2] for _ in range(3)]
+    assert dones == [False, False, True]
+    env.close()
+
+
+def test_vec_env_matches_host_engine_and_rollout():
+    import torch
+    from gym_flock_b200 import FlockVecEnv, HostFlockBatch
+    from gym_flock_b200.synthetic import initial_states
+    x0 = initial_states(6, 50, seed=5, min_dist=0.1)
+    for precision in ("fp64-exact", "fp64", "fp32"):
+        for env_id in ("FlockingRelative-v0", "Flocking-v0"):
+            vec = FlockVecEnv(env_id, num_envs=6, n_agents=50, precision=precision)
+            host = HostFlockBatch(6, 50, knn_obs=(env_id == "Flocking-v0"), precision=precision)
+            obs, net = vec.reset(x0)
+            host.set_state(x0)
+            for _ in range(5):
+                (obs, net), rew, done, _ = vec.step(vec.controller())
+                host.step(None)
+            torch.cuda.synchronize()
+            assert np.array_equal(vec.x.cpu().numpy(), host.x)
+            assert np.array_equal(net.cpu().numpy(), host.network)
+            assert np.array_equal(rew.cpu().numpy(), host.reward)
+            ref = host.obs if env_id == "Flocking-v0" else host.values
+            assert np.array_equal(obs.cpu().numpy(), ref)
+            # C-side rollout == per-step API
+            vec2 = FlockVecEnv(env_id, num_envs=6, n_agents=50, precision=precision)
+            vec2.reset(x0)
+            rewards = torch.zeros(5, 6, dtype=vec2.dtype, device=vec2.device)
+            vec2.rollout(5, rewards)
+            torch.cuda.synchronize()
+            assert torch.equal(vec2.x, vec.x) and torch.equal(vec2.values, vec.values)
+            assert torch.equal(rewards[-1], vec.reward)
+            host.close()
