@@ -180,8 +180,10 @@ int step_impl(const FlockParams *p, const double *x_in, const double *u_in, doub
     if (x_out && x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
     if (u_in && u_next == u_in) return fail(FLOCK_EINVAL, "u_next must not alias u_in");
     if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values) || misaligned(network) ||
-        misaligned(reward) || misaligned(u_next) || misaligned(obs))
-        return fail(FLOCK_EALIGN, "all device buffers must be 16-byte aligned");
+        misaligned(u_next) || misaligned(obs))
+        return fail(FLOCK_EALIGN, "device buffers (except reward) must be 16-byte aligned");
+    if (reward && (reinterpret_cast<uintptr_t>(reward) % sizeof(T)))
+        return fail(FLOCK_EALIGN, "reward must be aligned to its element size");
     if (pl.knn && !obs) pl.knn = false;
     pl.k.x_in = x_in; pl.k.u_in = u_in; pl.k.x_out = x_out; pl.k.u_next = u_next;
     pl.k.values = values; pl.k.network = network; pl.k.reward = reward; pl.k.obs = obs;

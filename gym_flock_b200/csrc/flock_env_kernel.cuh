@@ -293,8 +293,9 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     if (valid && sub == 0) {
         T f0 = A.f0, f3 = A.f3, sdx, sdy;
         if constexpr (TRICK) {
-            f0 = Tr<T>::fma_((T)deg, xi.z, -A.f0);
-            f3 = Tr<T>::fma_((T)deg, xi.w, -A.f3);
+            // the fast path's diagonal (r2 clamped to tiny) always passes r2 < R2, so A.f0 holds v_i once
+            f0 = Tr<T>::fma_((T)(deg + 1), xi.z, -A.f0);
+            f3 = Tr<T>::fma_((T)(deg + 1), xi.w, -A.f3);
             sdx = cen ? Tr<T>::fma_((T)N, xi.z, -(T)stats[g * 2 + 0]) : f0;
             sdy = cen ? Tr<T>::fma_((T)N, xi.w, -(T)stats[g * 2 + 1]) : f3;
         } else if constexpr (EXACT) {

@@ -42,7 +42,7 @@ def check_pass(x_ref, got_values, got_network, got_u, got_reward, kind, comm_rad
     errs["values"] = normwise(np.asarray(got_values)[ok], h["values"][ok]) if ok.any() else 0.0
     errs["network"] = normwise(np.asarray(got_network)[ok], h["adj_mean"][ok]) if ok.any() else 0.0
     oku = ~exempt_u_rows
-    den = max(np.max(np.abs(u)), 1e-2) if kind == "fp32" else np.max(np.abs(u))
+    den = max(np.max(np.abs(u)), 1e-2) if kind == "fp32" else max(np.max(np.abs(u)), 1e-300)
     errs["u"] = float(np.max(np.abs(np.asarray(got_u)[oku] - u[oku])) / den) if oku.any() else 0.0
     rw = c_oracle.reward(x_ref)
     errs["reward"] = abs(float(got_reward) - rw) / max(abs(rw), 1e-300)

@@ -20,20 +20,29 @@ def test_teacher_forced_and_free_running(precision, e, n, cen, knn, lanes):
     from gym_flock_b200.synthetic import initial_states
     from oracle import c_oracle
     kind = precision
-    x0 = initial_states(e, n, seed=4321 + n, min_dist=0.1 if n <= 100 else 0.0)
+    # states obey the reference's own reset() invariant (min pairwise distance >= 0.1, flocking_relative.py:160).
+    x0 = initial_states(e, n, seed=4321 + n, min_dist=0.1)
     steps = 200 if n <= 257 else 40
-    eng = HostFlockBatch(e, n, centralized=cen, knn_obs=knn, precision=precision, lanes=lanes)
+    # The centralized alignment term is -N*(v_i - mean v); explicit Euler multiplies a velocity deviation by
+    # (1 - N*dt) per unclipped step, so for N*dt > 2 the REFERENCE dynamics amplify any 1-ulp difference
+    # exponentially (1.57^200 at N=257): only the bit-exact mode can track a free-running rollout there.
+    # Non-exact modes are compared free-running in the stable regime N*dt <= 1 (dt = 0.01 up to N = 100).
+    dt = min(0.01, 1.0 / n)
+    eng = HostFlockBatch(e, n, centralized=cen, knn_obs=knn, precision=precision, lanes=lanes, dt=dt)
 
     # (i) teacher-forced along the reference trajectory
     x_ref, t_prev = x0, 0
+    worst = {}
     for t in (0, 1, 2, steps // 4, steps // 2, steps):
-        x_ref = c_oracle.rollout(x_ref, t - t_prev, centralized=cen)["x"] if t > t_prev else x_ref
+        x_ref = c_oracle.rollout(x_ref, t - t_prev, centralized=cen, dt=dt)["x"] if t > t_prev else x_ref
         t_prev = t
         eng.set_state(x_ref)
         u = eng.controller(cen)
         for k in range(e):
-            check_pass(x_ref[k], eng.values[k], eng.network[k], u[k], eng.reward[k], kind, centralized=cen,
-                       got_obs=None)
+            errs = check_pass(x_ref[k], eng.values[k], eng.network[k], u[k], eng.reward[k], kind, centralized=cen,
+                              got_obs=None)
+            for kk, vv in errs.items():
+                worst[kk] = max(worst.get(kk, 0), vv)
             if knn and n >= 7:
                 ref_obs = c_oracle.knn_obs(x_ref[k])
                 # neighbour ORDER may swap when two r2 differ by less than the working precision
@@ -42,7 +51,8 @@ def test_teacher_forced_and_free_running(precision, e, n, cen, knn, lanes):
                 assert rows_ok.mean() > 0.98, rows_ok.mean()
 
     # (ii) free-running with the device-side controller
-    ref = c_oracle.rollout(x0, steps, centralized=cen)
+    print("teacher-forced worst errors:", worst)
+    ref = c_oracle.rollout(x0, steps, centralized=cen, dt=dt)
     eng.set_state(x0)
     rewards = np.zeros((e, steps))
     for t in range(steps):
