@@ -202,7 +202,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     knn = cfg["env_id"] == "Flocking-v0"
     K, W = max(1, args.steps), max(3, args.warmup)
     x0 = initial_states_fast(E, N, seed=1234 + rank * E)
-    env = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=local_rank)
+    env = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=local_rank,
+                      adjacency_mode=args.adjacency)
     env.reset(x0)
     rewards = torch.zeros(K, E, dtype=env.dtype, device=env.device)
     env.rollout(W)
@@ -293,6 +294,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
+                    help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -127,7 +127,8 @@ def make_params(n_envs: int, n_agents: int, comm_radius: float = 0.9, dt: float 
     r2 = comm_radius * comm_radius if comm_radius2 is None else comm_radius2   # flocking_relative.py:44
     lo, hi = rows if rows is not None else (0, 0)
     return FlockParams(int(n_envs), int(n_agents), float(comm_radius), float(r2), float(dt),
-                       float(action_scalar), flags, int(knn), int(lo), int(hi), int(lanes), 0)
+                       float(action_scalar), flags, int(knn), int(lo), int(hi), int(lanes),
+                       int(os.environ.get("FLOCK_TUNE", "0")))
 
 
 def require_device() -> int:

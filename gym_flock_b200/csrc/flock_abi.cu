@@ -75,19 +75,22 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
 
     int G = 1, RT, tiles, threads;
     if (nrows == N && N * lanes <= 512) {
-        // whole envs per CTA: maximise lane utilisation x balance of CTAs over the SMs
+        // whole envs per CTA: maximise lane utilisation x occupancy x balance of CTAs over the resident slots
+        // (the kernels use <= 64 registers per thread: 1024 threads = 32 warps resident per SM)
         const int gmax = std::min(E, 512 / (N * lanes));
         double best = -1.0;
         for (int g = 1; g <= gmax; ++g) {
             const int thr = round_up32(g * N * lanes);
             const double util = (double)(g * N * lanes) / thr;
             const int ctas = (E + g - 1) / g;
-            const double per_sm = (double)ctas / kSMs;
-            const double bal = per_sm >= 1.0 ? per_sm / (double)((ctas + kSMs - 1) / kSMs) : 1.0;
-            // prefer >= 128 threads per CTA when there is a choice (fewer CTA launches per SM)
-            const double score = util * bal * (thr >= 128 ? 1.0 : 0.9);
+            const int per_sm = std::max(1, std::min(1024 / thr, 16));
+            const double occ = std::min(1.0, (double)(per_sm * thr) / 1024.0);
+            const double waves = (double)ctas / (double)(kSMs * per_sm);
+            const double bal = waves >= 1.0 ? waves / std::ceil(waves) : 1.0;
+            const double score = util * bal * (0.5 + 0.5 * occ);
             if (score > best + 1e-9) { best = score; G = g; }
         }
+        if ((p->reserved & 0xff) > 0 && (p->reserved & 0xff) <= gmax) G = p->reserved & 0xff;   // tuning override: envs per CTA
         RT = G * N; tiles = 1; threads = round_up32(RT * lanes);
     } else {
         if (nrows != N && E != 1 && false) return fail(FLOCK_EINVAL, "unreachable");
@@ -96,19 +99,22 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         threads = round_up32(RT * lanes);
         tiles = (nrows + RT - 1) / RT;
     }
-    const int W = ((N + lanes - 1) / lanes + 31) / 32;
-    const size_t v4 = (size_t)4 * tbytes;
-    const bool centre = (tbytes == 4);
+    const bool pa32 = (tbytes == 4);                   // fp32 output mode filters on packed fp32 positions
+    const int NP2 = (N + 1) / 2;
+    const int nk_max = pa32 ? 2 * ((NP2 + lanes - 1) / lanes) : (N + lanes - 1) / lanes;
+    const int W = (nk_max + 31) / 32;
     flock::KArgs &k = pl.k;
     memset(&k, 0, sizeof(k));
     k.off_xs = 0;
-    const size_t size_xs = (size_t)G * N * v4;
-    k.off_stage = k.off_masks = align16(size_xs);
-    const size_t size_stage = centre ? (size_t)G * N * 32 : 0;
+    const size_t size_xs = (size_t)G * N * 32;          // double4 per agent
+    k.off_pf = align16(size_xs);
+    const size_t size_pf = pa32 ? (size_t)G * NP2 * 16 : 0;
+    k.off_masks = align16(k.off_pf + size_pf);
     const size_t size_masks = (size_t)RT * lanes * W * 4;
-    k.off_invdeg = align16(k.off_masks + std::max(size_stage, size_masks));
-    k.off_stats = align16(k.off_invdeg + (size_t)RT * tbytes);
-    pl.smem = (size_t)k.off_stats + (size_t)G * 2 * 8;
+    k.off_stats = align16(k.off_masks + size_masks);
+    k.off_zero = align16(k.off_stats + (size_t)G * flock::STATS_PER_ENV * 8);
+    k.off_sort = align16(k.off_zero + flock::ZERO_BYTES);
+    pl.smem = (size_t)k.off_sort + (size_t)(flock::SORT_BINS + RT) * 4;
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
                     N, pl.smem, kMaxSmem);
@@ -119,11 +125,10 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         // Decentralized (:205-206): additionally r2 < R2, i.e. r2 <= pred(R2) when R2 <= R.
         const bool cen = k.centralized != 0;
         const double R = p->comm_radius, R2 = p->comm_radius2;
-        const float Rf = (float)R, R2f = (float)R2;
         k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
-        k.Rm_f = (cen || R2f > Rf) ? Rf : std::nextafterf(R2f, -1.0f);
     }
-    k.W = W; k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
+    k.tune = p->reserved >> 8;
+    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
     pl.lanes = lanes; pl.threads = threads;
     pl.grid = ((E + G - 1) / G) * tiles;
     return FLOCK_OK;
