@@ -73,52 +73,36 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         return fail(FLOCK_EINVAL, "lanes=%d must be a power of two <= 32", lanes);
     }
 
-    int G = 1, RT, tiles, threads;
-    if (nrows == N && N * lanes <= 512) {
-        // whole envs per CTA: maximise lane utilisation x occupancy x balance of CTAs over the resident slots
-        // (the kernels use <= 64 registers per thread: 1024 threads = 32 warps resident per SM)
-        const int gmax = std::min(E, 512 / (N * lanes));
-        double best = -1.0;
-        for (int g = 1; g <= gmax; ++g) {
-            const int thr = round_up32(g * N * lanes);
-            const double util = (double)(g * N * lanes) / thr;
-            const int ctas = (E + g - 1) / g;
-            const int per_sm = std::max(1, std::min(1024 / thr, 16));
-            const double occ = std::min(1.0, (double)(per_sm * thr) / 1024.0);
-            const double waves = (double)ctas / (double)(kSMs * per_sm);
-            const double bal = waves >= 1.0 ? waves / std::ceil(waves) : 1.0;
-            const double score = util * bal * (0.5 + 0.5 * occ);
-            if (score > best + 1e-9) { best = score; G = g; }
-        }
-        if ((p->reserved & 0xff) > 0 && (p->reserved & 0xff) <= gmax) G = p->reserved & 0xff;   // tuning override: envs per CTA
-        RT = G * N; tiles = 1; threads = round_up32(RT * lanes);
-    } else {
-        if (nrows != N && E != 1 && false) return fail(FLOCK_EINVAL, "unreachable");
-        threads = 256;
-        RT = std::min(threads / lanes, nrows);
-        threads = round_up32(RT * lanes);
-        tiles = (nrows + RT - 1) / RT;
-    }
+    // Rows per CTA window.  Small envs: flat windows over the E*nrows rows (every lane gets a row; a window stages
+    // the few envs it touches).  Envs with at least a window of rows: row tiles per env.
+    int threads = (lanes > 1) ? 256 : (N < 256 ? 128 : 256);
+    if ((p->reserved & 0xff) > 0) threads = std::min(512, 32 * (p->reserved & 0xff));     // tuning override
+    int RT = std::max(1, threads / lanes);
+    const long long rows_total = (long long)E * nrows;
+    if (rows_total < RT) RT = (int)rows_total;
+    threads = round_up32(RT * lanes);
+    int tiles, GMAX, grid;
+    if (nrows >= RT) { tiles = (nrows + RT - 1) / RT; GMAX = 1; grid = E * tiles; }
+    else { tiles = 0; GMAX = std::min(E, (RT - 1) / nrows + 2); grid = (int)((rows_total + RT - 1) / RT); }
     const bool pa32 = (tbytes == 4);                   // fp32 output mode filters on packed fp32 positions
     const int NP2 = (N + 1) / 2;
     const int nk_max = pa32 ? 2 * ((NP2 + lanes - 1) / lanes) : (N + lanes - 1) / lanes;
-    const int W = (nk_max + 31) / 32;
+    const int CAPL = std::min((nk_max + 1) & ~1, 48);   // candidate-list capacity per (row, lane); overflow -> all-pairs fallback
     flock::KArgs &k = pl.k;
     memset(&k, 0, sizeof(k));
     k.off_xs = 0;
-    const size_t size_xs = (size_t)G * N * 32;          // double4 per agent
+    const size_t size_xs = (size_t)GMAX * N * 32;       // double4 per agent
     k.off_pf = align16(size_xs);
-    const size_t size_pf = pa32 ? (size_t)G * NP2 * 16 : 0;
-    k.off_masks = align16(k.off_pf + size_pf);
-    const size_t size_masks = (size_t)RT * lanes * W * 4;
-    k.off_stats = align16(k.off_masks + size_masks);
-    k.off_zero = align16(k.off_stats + (size_t)G * flock::STATS_PER_ENV * 8);
-    k.off_sort = align16(k.off_zero + flock::ZERO_BYTES);
-    pl.smem = (size_t)k.off_sort + (size_t)(flock::SORT_BINS + RT) * 4;
+    const size_t size_pf = pa32 ? (size_t)GMAX * NP2 * 16 : 0;
+    k.off_lists = align16(k.off_pf + size_pf);
+    const size_t size_lists = (size_t)threads * (CAPL + 32) * 2;
+    k.off_stats = align16(k.off_lists + size_lists);
+    k.off_zero = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);
+    pl.smem = (size_t)k.off_zero + flock::ZERO_BYTES;
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
                     N, pl.smem, kMaxSmem);
-    k.E = E; k.N = N; k.G = G; k.RT = RT; k.tiles = tiles; k.row_lo = row_lo; k.row_hi = row_hi;
+    k.E = E; k.N = N; k.RT = RT; k.tiles = tiles; k.GMAX = GMAX; k.row_lo = row_lo; k.row_hi = row_hi;
     k.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
     {
         // fast-path gradient mask as ONE compare r2 <= Rm.  Centralized: r2 <= R (flocking_relative.py:225).
@@ -128,9 +112,9 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
     }
     k.tune = p->reserved >> 8;
-    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
+    k.CAPL = CAPL; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
     pl.lanes = lanes; pl.threads = threads;
-    pl.grid = ((E + G - 1) / G) * tiles;
+    pl.grid = grid;
     return FLOCK_OK;
 }
 

@@ -1,28 +1,29 @@
 // flock_env_kernel.cuh -- the env-resident fused flocking step (sm_100a), "filter then refine".
 //
-// One CTA owns either G whole environments (small N) or one row tile of one environment (large N);
-// either way the whole state x[N,4] of its environment(s) is staged in shared memory, so each ordered
-// pair (i,j) is visited exactly once per step.  Per env and step, in ONE launch:
+// A CTA owns a WINDOW of consecutive rows (agents i) of the flattened [E x rows] space -- small envs are packed
+// back to back so every lane has a row; large envs are cut into row tiles -- and stages the full state x[N,4] of
+// the environments its rows belong to in shared memory.  Each ordered pair (i,j) is visited exactly once per
+// step.  After ONE block barrier (state staged) every warp runs on its own:
 //
-//   zero-fill : the CTA's slice of the dense adj_mean output is cleared first with coalesced 16-byte
-//               stores (fire and forget: the HBM write overlaps everything below)
+//   zero-fill : lane 0 queues 1-D bulk (TMA) stores of a shared zero block over the warp's slice of the dense
+//               adj_mean output; the copy engine streams them to HBM while the warp computes
 //   prologue  : x' = integrate(x_in, u_in)                          flocking_relative.py:96-105
 //               reward = -(var vx' + var vy')                       flocking_relative.py:145-147
 //   phase A   : FILTER over all N^2 ordered pairs: r2 and one compare per pair, candidate bits
 //               (r2 <= max(R, R^2)) kept in shared memory.          flocking_relative.py:113-117
-//               fp32 output mode: packed f32x2 math on centroid-centred fp32 positions with a
-//               conservative threshold; fp64 modes: fp64 r2 (exact mode: NumPy's unfused r2).
+//               fp32 output mode: packed f32x2 math on fp32 positions relative to a per-env origin with a
+//               conservative per-row threshold; fp64 modes: fp64 r2 (exact mode: NumPy's unfused r2).
 //               Flocking-v0: a running top-8 by r2 rides along.     flocking.py:20-24
 //   phase B   : REFINE only the candidates (~deg of N) in fp64: exact adjacency bit, the 6 masked
 //               feature sums, the potential gradient.               flocking_relative.py:117-129,214-226
 //               EXACT: NumPy's operation order, separately rounded, IEEE divide, ascending j.
-//   epilogue  : values, u_next (clip, /10), obs; the few non-zero adj_mean entries (1/deg) are scattered
-//               into the zero-filled rows.                          flocking_relative.py:120-122,209-211
+//   epilogue  : values, u_next (clip, /10), obs; after the warp's bulk zero stores have completed, the few
+//               non-zero adj_mean entries (1/deg) are scattered into its rows.   flocking_relative.py:120-122,209-211
 //
 // Non-neighbour pairs contribute exact zeros to every masked sum of the reference, so skipping them in
 // phase B changes nothing (not even in EXACT mode, up to the sign of a zero).  The centralized alignment
 // term sum_j (v_i - v_j) runs over ALL j: EXACT accumulates it sequentially in phase A; the fast modes use
-// N*(v_i - mean) - sum_j (v_j - mean) in fp64 (O(N)).
+// N*(v_i - ref) - sum_j (v_j - ref) in fp64 (O(N), sums gathered while staging).
 //
 // LANES threads cooperate on one row (pairs interleaved across them, warp-shuffle reduction) so small
 // batches still fill 148 SMs.
@@ -42,26 +43,23 @@ struct KArgs {
     void *reward;
     void *obs;
     int E, N;
-    int G;        // envs per CTA
-    int RT;       // rows per CTA
-    int tiles;    // CTAs per env group
+    int RT;       // rows per CTA window
+    int tiles;    // 0: flat windows over E*nre rows; > 0: row tiles per env (windows never cross envs)
+    int GMAX;     // max envs a window touches (staging capacity)
     int row_lo, row_hi;
     int centralized;
-    int W;        // 32-bit candidate words per (row, lane)
+    int CAPL;     // candidate-list capacity per (row, lane) in entries (multiple of 2); lists hold CAPL + 32
     int NP2;      // pair slots per env in the packed fp32 position array: (N + 1) / 2
     double R, R2, dt, ascale;
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
-    unsigned off_xs, off_pf, off_masks, off_stats;
-    unsigned off_zero;   // ZERO_BYTES of zeros: source of the bulk (TMA) zero-fill of the dense adjacency
-    unsigned off_sort;   // LANES == 1: hist[SORT_BINS] + perm[RT] for the candidate-count row sort
-    int tune;            // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 plain-store fill
+    unsigned off_xs, off_pf, off_lists, off_stats, off_zero;
+    int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter
 };
 
-constexpr int ZERO_BYTES = 8192;
-constexpr int SORT_BINS = 64;
+constexpr int ZERO_BYTES = 2048;   // shared zero block: source of the bulk (TMA) zero-fill of the dense adjacency
 
-// ---- bulk async copy (TMA, 1-D) shared -> global, used to clear the dense adjacency slice in the background ----
+// ---- bulk async copy (TMA, 1-D) shared -> global ------------------------------------------------------------
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
@@ -71,7 +69,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-constexpr int STATS_PER_ENV = 6;   // mean vx, mean vy, residual sum vx, residual sum vy, thrA, (pad)
+// shared-memory double accumulate (a handful per env and CTA; CAS loop is fine)
+__device__ __forceinline__ void smem_add(double *p, double v) { atomicAdd(p, v); }
+
+constexpr int STATS_PER_ENV = 4;   // ref vx, ref vy, S vx, S vy (sums of v - ref over the env)
 constexpr int TOPK = KNN_K + 1;    // the diagonal (r2 = 0) rides along and is dropped at the end
 
 template <typename T> struct TopK {
@@ -149,6 +150,17 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
     return a;
 }
 
+// The adjacency decision alone, bit-identical to what refine_exact / refine_fast decide (overflow fallback).
+template <bool EXACT> __device__ __forceinline__ bool adj_only(const double4 xi, const double4 xj, const double R2) {
+    if constexpr (EXACT) {
+        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+        return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < R2;
+    } else {
+        const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+        return fma(dx, dx, dy * dy) < R2;
+    }
+}
+
 template <typename TO, int LANES, bool EXACT, bool KNN>
 __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     constexpr bool PA32 = std::is_same<TO, float>::value;   // phase A on packed fp32 positions
@@ -157,332 +169,257 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
 
     extern __shared__ __align__(16) unsigned char smem[];
     double4 *xs = reinterpret_cast<double4 *>(smem + a.off_xs);
-    float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf);       // (px_2m, px_2m+1, py_2m, py_2m+1), centred
-    unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);
+    float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf);       // (px_2m, px_2m+1, py_2m, py_2m+1) - env origin
+    unsigned short *lists = reinterpret_cast<unsigned short *>(smem + a.off_lists);
     double *stats = reinterpret_cast<double *>(smem + a.off_stats);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int lane = tid & 31;
     const int N = a.N;
-    const int grp = blockIdx.x / a.tiles, tile = blockIdx.x - grp * a.tiles;
-    const int env0 = grp * a.G;
-    const int genv = min(a.G, a.E - env0);
-    const int nag = genv * N;
-    const bool writer = (tile == 0);
-    const int nrows_env = a.row_hi - a.row_lo;
-    const int rows_cta = min(a.RT, genv * nrows_env - tile * a.RT);     // rows this CTA owns (>= 1)
+    const int nre = a.row_hi - a.row_lo;                    // rows per env handled by this call
+    // ---- the CTA's window of flat rows [r0, r1) and the envs [e0, e0 + nenv) it touches -------------------
+    int r0, r1;
+    if (a.tiles > 0) {
+        const int e = blockIdx.x / a.tiles, t = blockIdx.x - e * a.tiles;
+        r0 = e * nre + t * a.RT;
+        r1 = min(r0 + a.RT, (e + 1) * nre);
+    } else {
+        r0 = blockIdx.x * a.RT;
+        r1 = min(r0 + a.RT, a.E * nre);
+    }
+    const int e0 = r0 / nre;
+    const int nenv = (r1 - 1) / nre - e0 + 1;
     TO *net = reinterpret_cast<TO *>(a.network);
-    // rows [row_lo + tile*RT, +rows_cta) of env0.. are consecutive in memory (with G > 1 there is one tile and
-    // row_lo = 0): the CTA's slice of the dense output is ONE contiguous run of rows_cta*N elements.
-    const size_t net_base = ((size_t)env0 * N + (size_t)a.row_lo + (size_t)tile * a.RT) * N;
+    TO *reward = reinterpret_cast<TO *>(a.reward);
 
-    // ---- zero source for the bulk fill + sort histogram ------------------------------------------------
+    // ---- zero block for the bulk fill, per-env accumulators ---------------------------------------------------
     {
         float4 *zb = reinterpret_cast<float4 *>(smem + a.off_zero);
         for (int q = tid; q < ZERO_BYTES / 16; q += nthr) zb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LANES == 1) for (int q = tid; q < SORT_BINS; q += nthr) reinterpret_cast<int *>(smem + a.off_sort)[q] = 0;
-        fence_async_smem();      // make the generic-proxy zeros visible to the async proxy (TMA) before the barrier
+        fence_async_smem();      // generic-proxy zeros -> visible to the async proxy (TMA) after the barrier
+        if constexpr (!EXACT) {
+            for (int q = tid; q < nenv * STATS_PER_ENV; q += nthr) stats[q] = 0.0;
+            __syncthreads();     // accumulators are added to below
+        }
     }
 
-    // ---- prologue: load, integrate, publish x', stage -------------------------------------------------
-    for (int idx = tid; idx < nag; idx += nthr) {
-        const size_t grow = (size_t)env0 * N + idx;
-        double4 x = ld_state(a.x_in + grow * 4);
-        if (a.u_in) {
-            const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + grow);
-            x = integrate_exact(x, u, a.dt, a.ascale);
+    // ---- prologue: load, integrate, publish x', stage; gather per-env velocity sums -----------------------------
+    for (int ge = 0; ge < nenv; ++ge) {
+        const int env = e0 + ge;
+        const bool writer = (r0 <= env * nre) && (env * nre < r1);     // this CTA holds the env's first row
+        const double4 ref = ld_state(a.x_in + (size_t)env * N * 4);    // origin: agent 0 before integration
+        double sx = 0, sy = 0;
+        for (int j = tid; j < N; j += nthr) {
+            const size_t ga = (size_t)env * N + j;
+            double4 x = ld_state(a.x_in + ga * 4);
+            if (a.u_in) {
+                const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + ga);
+                x = integrate_exact(x, u, a.dt, a.ascale);
+            }
+            if (a.x_out && writer) st_state(a.x_out + ga * 4, x);
+            xs[ge * N + j] = x;
+            if constexpr (!EXACT) { sx += x.z - ref.z; sy += x.w - ref.w; }
+            if constexpr (PA32) {
+                float *p = reinterpret_cast<float *>(pf + (size_t)ge * a.NP2 + (j >> 1));
+                p[j & 1] = (float)(x.x - ref.x); p[2 + (j & 1)] = (float)(x.y - ref.y);
+                if ((N & 1) && j == N - 1) { p[1] = CUDART_INF_F; p[3] = CUDART_INF_F; }   // odd N: pad slot at infinity
+            }
         }
-        if (a.x_out && writer) st_state(a.x_out + grow * 4, x);
-        xs[idx] = x;
+        if constexpr (!EXACT) {
+            if (tid - lane < N) {           // warps that staged agents of this env (uniform per warp)
+                sx = warp_sum(sx); sy = warp_sum(sy);
+                if (lane == 0) {
+                    double *st = stats + ge * STATS_PER_ENV;
+                    smem_add(st + 2, sx); smem_add(st + 3, sy);
+                    if (tid == 0) { st[0] = ref.z; st[1] = ref.w; }
+                }
+            }
+        }
     }
     __syncthreads();
+    // ==== from here on warps are independent ======================================================================
 
-    // ---- zero-fill of the dense adj_mean slice: ONE thread queues 1-D bulk (TMA) stores of the shared zero block;
-    // the copy engine streams them to HBM while every warp computes.  Unaligned head/tail elements: plain stores.
-    if (net) {
-        TO *out = net + net_base;
-        const int total = rows_cta * N;
-        constexpr int VEC = 16 / (int)sizeof(TO);
-        const int head = min((int)((VEC - (net_base % VEC)) % VEC), total);
-        const int nvec = (total - head) / VEC;
-        if (tid < head) out[tid] = TO(0);
-        if (tid < total - (head + nvec * VEC)) out[head + nvec * VEC + tid] = TO(0);
-        if (a.tune & 4) {
-            float4 *o4 = reinterpret_cast<float4 *>(out + head);
-            for (int q = tid; q < nvec; q += nthr) o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (tid == 0 && !(a.tune & 1)) {
-            char *dst = reinterpret_cast<char *>(out + head);
-            const size_t bytes = (size_t)nvec * 16;
-            for (size_t off = 0; off < bytes; off += ZERO_BYTES)
-                bulk_store_s2g(dst + off, smem + a.off_zero, (unsigned)min((size_t)ZERO_BYTES, bytes - off));
-            bulk_commit();
-        }
-    }
-
-    // ---- per-env statistics, one warp per env: reward, velocity mean (alignment trick), fp32 positions ----
-    TO *reward = reinterpret_cast<TO *>(a.reward);
-    for (int g = warp; g < genv; g += nwarps) {
-        const double4 *xe = xs + g * N;
-        if constexpr (EXACT) {
-            if (lane == 0 && reward && writer) {      // NumPy's two-pass variance, sequential sums
-                double sx = 0.0, sy = 0.0;
-                for (int j = 0; j < N; ++j) { sx = __dadd_rn(sx, xe[j].z); sy = __dadd_rn(sy, xe[j].w); }
-                const double mx = __ddiv_rn(sx, (double)N), my = __ddiv_rn(sy, (double)N);
-                double qx = 0.0, qy = 0.0;
-                for (int j = 0; j < N; ++j) {
-                    const double ex = __dsub_rn(xe[j].z, mx), ey = __dsub_rn(xe[j].w, my);
-                    qx = __dadd_rn(qx, __dmul_rn(ex, ex)); qy = __dadd_rn(qy, __dmul_rn(ey, ey));
-                }
-                reward[env0 + g] = __dmul_rn(-1.0, __dadd_rn(__ddiv_rn(qx, (double)N), __ddiv_rn(qy, (double)N)));
-            }
-        } else {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int j = lane; j < N; j += 32) { const double4 v = xe[j]; s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w; }
-            const double invN = 1.0 / (double)N;
-            const double m0 = warp_sum(s0) * invN, m1 = warp_sum(s1) * invN;
-            const double m2 = warp_sum(s2) * invN, m3 = warp_sum(s3) * invN;
-            double qx = 0, qy = 0, rx = 0, ry = 0;
-            float pmax = 0.f;
-            for (int j = lane; j < N; j += 32) {
-                const double4 v = xe[j];
-                const double ex = v.z - m2, ey = v.w - m3;
-                qx = fma(ex, ex, qx); qy = fma(ey, ey, qy);
-                rx += ex; ry += ey;
-                if constexpr (PA32) {
-                    const float cx = (float)(v.x - m0), cy = (float)(v.y - m1);
-                    pmax = fmaxf(pmax, fmaxf(fabsf(cx), fabsf(cy)));
-                    float *p = reinterpret_cast<float *>(pf + (size_t)g * a.NP2 + (j >> 1));
-                    p[j & 1] = cx; p[2 + (j & 1)] = cy;
-                }
-            }
-            qx = warp_sum(qx); qy = warp_sum(qy); rx = warp_sum(rx); ry = warp_sum(ry);
-            if constexpr (PA32) {
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, m));
-            }
-            if (lane == 0) {
-                double *st = stats + g * STATS_PER_ENV;
-                st[0] = m2; st[1] = m3; st[2] = rx; st[3] = ry;
-                if constexpr (PA32) {
-                    // conservative fp32 candidate threshold: every pair with true r2 <= thrC passes.  Coordinates
-                    // are rounded to within pmax*2^-24 each; |d(r2)| <= 2(|dx|+|dy|)*2*that + a few ulp of r2.
-                    const float tc = (float)a.thrC;
-                    st[4] = (double)(tc * (1.0f + 2e-6f) + 16.0f * sqrtf(tc) * pmax * 1.1920929e-7f + 1e-30f);
-                    if (N & 1) {       // pad the odd slot with an agent at infinity: r2 = inf, never a candidate
-                        float *p = reinterpret_cast<float *>(pf + (size_t)g * a.NP2 + (N >> 1));
-                        p[1] = CUDART_INF_F; p[3] = CUDART_INF_F;
+    // ---- rewards: the CTA holding an env's first row computes it, one warp per env -----------------------------------
+    if (reward) {
+        const int warp = tid >> 5, nwarps = nthr >> 5;
+        for (int ge = warp; ge < nenv; ge += nwarps) {
+            const int env = e0 + ge;
+            if (!((r0 <= env * nre) && (env * nre < r1))) continue;
+            const double4 *xe = xs + ge * N;
+            if constexpr (EXACT) {
+                if (lane == 0) {            // NumPy's two-pass variance with sequential sums (:145-147)
+                    double sx = 0.0, sy = 0.0;
+                    for (int j = 0; j < N; ++j) { sx = __dadd_rn(sx, xe[j].z); sy = __dadd_rn(sy, xe[j].w); }
+                    const double mx = __ddiv_rn(sx, (double)N), my = __ddiv_rn(sy, (double)N);
+                    double qx = 0.0, qy = 0.0;
+                    for (int j = 0; j < N; ++j) {
+                        const double ex = __dsub_rn(xe[j].z, mx), ey = __dsub_rn(xe[j].w, my);
+                        qx = __dadd_rn(qx, __dmul_rn(ex, ex)); qy = __dadd_rn(qy, __dmul_rn(ey, ey));
                     }
+                    reward[env] = __dmul_rn(-1.0, __dadd_rn(__ddiv_rn(qx, (double)N), __ddiv_rn(qy, (double)N)));
                 }
-                if (reward && writer) reward[env0 + g] = (TO)(-(qx + qy) * invN);
+            } else {
+                const double *st = stats + ge * STATS_PER_ENV;
+                const double invN = 1.0 / (double)N;
+                const double mx = fma(st[2], invN, st[0]), my = fma(st[3], invN, st[1]);
+                double qx = 0, qy = 0;
+                for (int j = lane; j < N; j += 32) {
+                    const double ex = xe[j].z - mx, ey = xe[j].w - my;
+                    qx = fma(ex, ex, qx); qy = fma(ey, ey, qy);
+                }
+                qx = warp_sum(qx + qy);
+                if (lane == 0) reward[env] = (TO)(-qx * invN);
             }
         }
     }
-    if constexpr (!EXACT) __syncthreads();
 
     // ---- row assignment -----------------------------------------------------------------------------------
-    const int rl0 = tid / LANES, sub = tid % LANES;
-    const int fr0 = tile * a.RT + rl0;                     // flat row over the group's rows
-    const bool valid0 = (rl0 < a.RT) && (fr0 < genv * nrows_env);
-    const int g0 = valid0 ? fr0 / nrows_env : 0;
-    const int i0 = valid0 ? a.row_lo + (fr0 - g0 * nrows_env) : 0;
+    const int rl = tid / LANES, sub = tid % LANES;
+    const int fr = r0 + rl;                                 // flat row
+    const bool valid = fr < r1;
+    int g = 0;
+    if (valid && nenv > 1) {                                // env of this row, relative to e0 (exact float division:
+        const int lr = fr - e0 * nre;                       //   lr < RT + nre <= 2^17, see host plan)
+        g = (int)__fdividef((float)lr + 0.5f, (float)nre);
+    }
+    const int env = e0 + g;
+    const int i = valid ? a.row_lo + (fr - env * nre) : 0;
     const bool cen = a.centralized != 0;
+    const double4 *xe = xs + g * N;
+    const double4 xi = xe[i];
+    unsigned short *lst = lists + (size_t)tid * (a.CAPL + 32);
+    const size_t grow = (size_t)env * N + i;                // global row (agent) index
+
+    // ---- per-warp bulk zero-fill of the warp's rows of the dense adjacency ---------------------------------------
+    // The rows of a warp are consecutive flat rows; with full rows (nre == N) they are ONE contiguous run in
+    // memory, otherwise one run per env they belong to.  Lane l queues the l-th 2 KB piece of the run.
+    bool bulk_pending = false;
+    if (net && !(a.tune & 1)) {
+        const int wr0 = r0 + (tid - lane) / LANES;                           // first flat row of this warp
+        const int wr1 = min(wr0 + 32 / LANES, r1);
+        int s0 = wr0;
+        while (s0 < wr1) {                                                   // runs (1 unless rows are sharded)
+            const int senv = s0 / nre;
+            const int s1 = (nre == N) ? wr1 : min(wr1, (senv + 1) * nre);
+            const size_t base = ((size_t)senv * N + a.row_lo + (s0 - senv * nre)) * N;
+            const unsigned total = (unsigned)(s1 - s0) * (unsigned)N;
+            constexpr unsigned VEC = 16 / (unsigned)sizeof(TO);
+            const unsigned headn = min((unsigned)((VEC - (unsigned)(base & (VEC - 1))) & (VEC - 1)), total);
+            const unsigned nvec = (total - headn) / VEC;
+            TO *out = net + base;
+            if ((unsigned)lane < headn) out[lane] = TO(0);
+            if ((unsigned)lane < total - (headn + nvec * VEC)) out[headn + nvec * VEC + lane] = TO(0);
+            char *dst = reinterpret_cast<char *>(out + headn);
+            const unsigned bytes = nvec * 16u;
+            for (unsigned off = (unsigned)lane * ZERO_BYTES; off < bytes; off += 32u * ZERO_BYTES) {
+                bulk_store_s2g(dst + off, smem + a.off_zero, min((unsigned)ZERO_BYTES, bytes - off));
+                bulk_pending = true;
+            }
+            s0 = s1;
+        }
+        if (bulk_pending) bulk_commit();
+    }
 
     Acc A;
     A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
+    TopK<TK> top;
+    if constexpr (KNN) top.init(i);
 
-    // ---- phase A: filter ----------------------------------------------------------------------------------
-    // Each lane owns bit positions k = 0.. of its words; j_of(k) maps them to agents.
-    //   fp32 packed : pair slot m = sub + LANES*(k>>1), agent j = 2m + (k&1)
+    // ---- phase A: filter; candidates are appended to this lane's list (ascending j) ---------------------------------
+    //   fp32 packed : pair slot m = sub + LANES*t, agents j = 2m, 2m+1
     //   fp64        : j = sub + LANES*k
-    int cnt = 0;                                           // candidates found by this lane
-    {
-        const int g = g0, i = i0;
-        const double4 *xe = xs + g * N;
-        const double4 xi = xe[i];
-        unsigned *mrow = masks + (size_t)(rl0 * LANES + sub) * a.W;
-        TopK<TK> top;
-        if constexpr (KNN) top.init(i);
-        if constexpr (PA32) {
-            const int nslots = valid0 ? (a.NP2 - sub + LANES - 1) / LANES : 0;
-            const float4 *pe = pf + (size_t)g * a.NP2;
-            const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
-            const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
-            const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
-            const float thrA = (float)stats[g * STATS_PER_ENV + 4];
-            for (int w = 0; w * 16 < nslots; ++w) {
-                unsigned bits = 0;
-                const int tbase = w * 16;
-                const int tend = min(16, nslots - tbase);
-                auto body = [&](const int tt) {
-                    const int m = sub + LANES * (tbase + tt);
-                    const float4 q = pe[m];
-                    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
-                    const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
-                    const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-                    bits |= (r2.x <= thrA) ? (1u << (2 * tt)) : 0u;
-                    bits |= (r2.y <= thrA) ? (2u << (2 * tt)) : 0u;
-                    if constexpr (KNN) { top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1); }
-                };
-                if (tend == 16) {
+    unsigned short *lp = lst;                               // append pointer
+    unsigned short *const lend = lst + a.CAPL;              // soft capacity (a chunk may run 32 past it)
+    bool overflow = false;
+    if constexpr (PA32) {
+        const int nslots = valid ? (a.NP2 - sub + LANES - 1) / LANES : 0;
+        const float4 *pe = pf + (size_t)g * a.NP2;
+        const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
+        const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
+        const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
+        // Conservative per-row fp32 threshold: every pair with true r2 <= thrC passes.  For such a pair
+        // |p_j|inf <= |p_i|inf + rc (rc = sqrt(thrC)); each coordinate is rounded to <= |p|*2^-24, so
+        // |d(dx)| <= (2|p_i|inf + 3rc)*2^-24 and |d(r2)| <= 4 rc |d(dx)| + a few ulp(r2).
+        const float tc = (float)a.thrC, rc = sqrtf(tc);
+        const float thrA = tc * (1.0f + 2e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+        for (int tbase = 0; tbase < nslots; tbase += 16) {
+            const int tend = min(16, nslots - tbase);
+            auto body = [&](const int tt) {
+                const int m = sub + LANES * (tbase + tt);
+                const float4 q = pe[m];
+                const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+                if (r2.x <= thrA) { *lp = (unsigned short)(2 * m); ++lp; }
+                if (r2.y <= thrA) { *lp = (unsigned short)(2 * m + 1); ++lp; }
+                if constexpr (KNN) { top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1); }
+            };
+            if (tend == 16) {
 #pragma unroll
-                    for (int tt = 0; tt < 16; ++tt) body(tt);
-                } else {
-                    for (int tt = 0; tt < tend; ++tt) body(tt);
-                }
-                mrow[w] = bits;
-                cnt += __popc(bits);
+                for (int tt = 0; tt < 16; ++tt) body(tt);
+            } else {
+                for (int tt = 0; tt < tend; ++tt) body(tt);
             }
-        } else {
-            const int nk = valid0 ? (N - sub + LANES - 1) / LANES : 0;
-            const double thrC = a.thrC;
-            for (int w = 0; w * 32 < nk; ++w) {
-                unsigned bits = 0;
-                const int kbase = w * 32;
-                const int kend = min(32, nk - kbase);
-                auto body = [&](const int kk) {
-                    const int j = sub + LANES * (kbase + kk);
-                    const double4 xj = xe[j];
-                    double r2;
-                    bool c;
-                    if constexpr (EXACT) {
-                        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
-                        r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        c = (r2 < a.R2) || !(r2 > a.R);
-                        if (cen) {   // sum_j (v_i - v_j) over ALL j, sequential (flocking_relative.py:204-208)
-                            A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));
-                            A.s1 = __dadd_rn(A.s1, __dsub_rn(xi.w, xj.w));
-                        }
-                    } else {
-                        const double dx = xi.x - xj.x, dy = xi.y - xj.y;
-                        r2 = fma(dx, dx, dy * dy);
-                        c = r2 <= thrC;
-                    }
-                    bits |= c ? (1u << kk) : 0u;
-                    if constexpr (KNN) top.insert(r2, j);
-                };
-                if (kend == 32) {
-#pragma unroll 8
-                    for (int kk = 0; kk < 32; ++kk) body(kk);
-                } else {
-                    for (int kk = 0; kk < kend; ++kk) body(kk);
-                }
-                mrow[w] = bits;
-                cnt += __popc(bits);
-            }
+            if (lp > lend) { overflow = true; lp = lst; }   // too dense for the list: fall back to all pairs
         }
-
-        // ---- kNN observation (independent of phase B): merge the LANES partial lists, drop the diagonal,
-        //      obs[i, 4m:4m+4] = x_i - x_nbr(m)                                              flocking.py:20-24
-        if constexpr (KNN) {
-            int nb[TOPK];
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) {
-                if constexpr (LANES > 1) {
-                    TK bd = top.d[0]; int bi = top.id[0];
-#pragma unroll
-                    for (int s = LANES / 2; s > 0; s >>= 1) {
-                        const TK od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
-                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-                    }
-                    if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
-                    nb[m] = bi;
-                } else {
-                    nb[m] = top.id[m];
-                }
-            }
-            if (valid0 && sub == 0 && a.obs) {
-                TO *o = reinterpret_cast<TO *>(a.obs) + ((size_t)(env0 + g) * N + i) * (NXS * KNN_K);
-                int m = 0;
-                bool dropped = false;
-#pragma unroll
-                for (int q = 0; q < TOPK; ++q) {
-                    if (!dropped && nb[q] == i) { dropped = true; continue; }     // the diagonal (or an unused slot)
-                    if (m < KNN_K) {
-                        const double4 xn = xe[nb[q]];
-                        if constexpr (EXACT) {
-                            o[m * 4 + 0] = __dsub_rn(xi.x, xn.x); o[m * 4 + 1] = __dsub_rn(xi.y, xn.y);
-                            o[m * 4 + 2] = __dsub_rn(xi.z, xn.z); o[m * 4 + 3] = __dsub_rn(xi.w, xn.w);
-                        } else {
-                            o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                            o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
-                        }
-                        ++m;
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- balance phase B: counting sort of the CTA's rows by candidate count (LANES == 1) -------------------
-    // Neighbour counts vary a lot from row to row; lanes of a warp would idle until its busiest row is done.
-    // After the sort every warp works on rows with (nearly) equal counts.  EXACT keeps the identity mapping only
-    // when the centralized alignment sums (held in this thread's registers) must stay with their row.
-    int rl = rl0;
-    bool valid = valid0;
-    constexpr bool SORT = (LANES == 1) && !EXACT;
-    if constexpr (SORT) {
-        int *hist = reinterpret_cast<int *>(smem + a.off_sort);
-        int *perm = hist + SORT_BINS;
-        const int bin = min(cnt, SORT_BINS - 1);
-        int rank = 0;
-        if (valid0) rank = atomicAdd(&hist[bin], 1);
-        __syncthreads();
-        if (warp == 0) {                                    // exclusive scan of the 64 bins, two per lane
-            const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
-            int v = h0 + h1;
-#pragma unroll
-            for (int m = 1; m < 32; m <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, m); if (lane >= m) v += t; }
-            const int excl = v - (h0 + h1);
-            hist[2 * lane] = excl; hist[2 * lane + 1] = excl + h0;
-        }
-        __syncthreads();
-        if (valid0) perm[hist[bin] + rank] = rl0;
-        __syncthreads();
-        valid = tid < rows_cta;
-        rl = valid ? perm[rows_cta - 1 - tid] : 0;          // heaviest rows first
-    }
-    const int fr = tile * a.RT + rl;
-    const int g = valid ? fr / nrows_env : 0;
-    const int i = valid ? a.row_lo + (fr - g * nrows_env) : 0;
-    const double4 *xe = xs + g * N;
-    const double4 xi = xe[i];
-    unsigned *mrow = masks + (size_t)(rl * LANES + sub) * a.W;
-    int nk;
-    if constexpr (PA32) nk = valid ? 2 * ((a.NP2 - sub + LANES - 1) / LANES) : 0;
-    else nk = valid ? (N - sub + LANES - 1) / LANES : 0;
-    const int nw = (nk + 31) >> 5;
-    auto j_of = [&](const int k) -> int {
-        if constexpr (PA32) return 2 * (sub + LANES * (k >> 1)) + (k & 1);
-        else return sub + LANES * k;
-    };
-
-    // ---- phase B: refine the candidates in fp64, ascending j per lane; rewrite the words with the exact bits ----
-    // ONE flat loop over this lane's candidates (not a loop per word): lanes advance through their words
-    // independently, so a warp iterates max-over-lanes(total candidates) times, not sum-over-words(max).
-    int deg = 0;
-    {
-        int w = 0;
-        bool more = nw > 0;
-        unsigned cand = more ? mrow[0] : 0u, ex = 0;
-        for (;;) {
-            while (more && cand == 0) {                     // word exhausted: publish its exact bits, fetch the next
-                mrow[w] = ex; deg += __popc(ex); ex = 0;
-                ++w; more = w < nw;
-                if (more) cand = mrow[w];
-            }
-            if (!more) break;
-            const int k = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const int j = j_of(w * 32 + k);
-            if (j != i) {                                   // diagonal: r2 = +inf in the reference (:115)
+    } else {
+        const int nk = valid ? (N - sub + LANES - 1) / LANES : 0;
+        const double thrC = a.thrC;
+        for (int kbase = 0; kbase < nk; kbase += 32) {
+            const int kend = min(32, nk - kbase);
+            auto body = [&](const int kk) {
+                const int j = sub + LANES * (kbase + kk);
                 const double4 xj = xe[j];
-                bool adj;
-                if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
-                else adj = refine_fast(xi, xj, a.R2, a.Rm, A);
-                ex |= adj ? (1u << k) : 0u;
+                double r2;
+                bool c;
+                if constexpr (EXACT) {
+                    const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+                    r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    c = (r2 < a.R2) || !(r2 > a.R);
+                    if (cen) {       // sum_j (v_i - v_j) over ALL j, sequential (flocking_relative.py:204-208)
+                        A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));
+                        A.s1 = __dadd_rn(A.s1, __dsub_rn(xi.w, xj.w));
+                    }
+                } else {
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    r2 = fma(dx, dx, dy * dy);
+                    c = r2 <= thrC;
+                }
+                if (c) { *lp = (unsigned short)j; ++lp; }
+                if constexpr (KNN) top.insert(r2, j);
+            };
+            if (kend == 32) {
+#pragma unroll 8
+                for (int kk = 0; kk < 32; ++kk) body(kk);
+            } else {
+                for (int kk = 0; kk < kend; ++kk) body(kk);
             }
+            if (lp > lend) { overflow = true; lp = lst; }
         }
     }
+
+    // ---- phase B: refine the candidates in fp64, ascending j per lane; neighbours are compacted in place ------------
+    int deg = 0;
+    auto refine = [&](const int j) -> bool {
+        const double4 xj = xe[j];
+        if constexpr (EXACT) return refine_exact(xi, xj, a.R, a.R2, cen, A);
+        else return refine_fast(xi, xj, a.R2, a.Rm, A);
+    };
+    if (!overflow) {
+        const int ncand = (int)(lp - lst);
+        for (int c = 0; c < ncand; ++c) {
+            const int j = lst[c];
+            if (j != i && refine(j)) { lst[deg] = (unsigned short)j; ++deg; }   // diagonal: r2 = +inf in the reference (:115)
+        }
+    } else if (valid) {                                     // rare: more candidates than the list holds
+        if constexpr (PA32) {
+            for (int m = sub; m < a.NP2; m += LANES)
+                for (int h = 0; h < 2; ++h) { const int j = 2 * m + h; if (j < N && j != i && refine(j)) ++deg; }
+        } else {
+            for (int j = sub; j < N; j += LANES) if (j != i && refine(j)) ++deg;
+        }
+    }
+    int degl = deg;                                         // neighbours found by this lane
 
     // ---- reduce across the LANES threads of a row ----------------------------------------------------------
     if constexpr (LANES > 1) {
@@ -496,7 +433,6 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     }
 
     // ---- row epilogue: features, action, 1/deg ---------------------------------------------------------------
-    const size_t grow = (size_t)(env0 + g) * N + i;
     TO idg;
     if constexpr (EXACT) idg = __ddiv_rn(1.0, (double)max(deg, 1));               // :121-122
     else if constexpr (PA32) idg = __frcp_rn((float)max(deg, 1));
@@ -515,7 +451,7 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
                 ux = __ddiv_rn(ux, a.ascale); uy = __ddiv_rn(uy, a.ascale);           // :211
             } else {
                 const double *st = stats + g * STATS_PER_ENV;
-                // centralized: sum_j (v_i - v_j) = N*(v_i - mean) - sum_j (v_j - mean); decentralized: masked sum = f0/f3
+                // centralized: sum_j (v_i - v_j) = N*(v_i - ref) - sum_j (v_j - ref); decentralized: masked sum = f0/f3
                 const double sdx = cen ? fma((double)N, xi.z - st[0], -st[2]) : A.f0;
                 const double sdy = cen ? fma((double)N, xi.w - st[1], -st[3]) : A.f3;
                 const double ia = Tr<double>::rcp(a.ascale);     // 1/10 to ~1 ulp; one extra rounding vs a true divide
@@ -526,23 +462,65 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
         }
     }
 
-    // ---- scatter the non-zero adj_mean entries (1/deg) into the zero-filled rows -------------------------------
-    // Thread 0 waits for the bulk zero stores of this CTA to complete, orders them (async proxy) before the
-    // generic-proxy stores below, then the barrier releases everybody.  Each CTA only touches its own slice.
+    // ---- kNN observation: merge the LANES partial lists, drop the diagonal, obs[i, 4m:4m+4] = x_i - x_nbr(m) ----
+    if constexpr (KNN) {
+        int nb[TOPK];
+#pragma unroll
+        for (int m = 0; m < TOPK; ++m) {
+            if constexpr (LANES > 1) {
+                TK bd = top.d[0]; int bi = top.id[0];
+#pragma unroll
+                for (int s = LANES / 2; s > 0; s >>= 1) {
+                    const TK od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                }
+                if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
+                nb[m] = bi;
+            } else {
+                nb[m] = top.id[m];
+            }
+        }
+        if (valid && sub == 0 && a.obs) {
+            TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
+            int m = 0;
+            bool dropped = false;
+#pragma unroll
+            for (int q = 0; q < TOPK; ++q) {
+                if (!dropped && nb[q] == i) { dropped = true; continue; }     // the diagonal (or an unused slot)
+                if (m < KNN_K) {
+                    const double4 xn = xe[nb[q]];
+                    if constexpr (EXACT) {
+                        o[m * 4 + 0] = __dsub_rn(xi.x, xn.x); o[m * 4 + 1] = __dsub_rn(xi.y, xn.y);
+                        o[m * 4 + 2] = __dsub_rn(xi.z, xn.z); o[m * 4 + 3] = __dsub_rn(xi.w, xn.w);
+                    } else {
+                        o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                        o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+                    }
+                    ++m;
+                }
+            }
+        }
+    }
+
+    // ---- scatter the non-zero adj_mean entries (1/deg) into the warp's zero-filled rows --------------------------
+    // Every lane that queued bulk zero stores waits for them and orders them (async proxy) before the generic-proxy
+    // stores below; __syncwarp then releases the warp.  A warp only ever touches its own rows.
     if (net == nullptr) return;
-    if (tid == 0) { bulk_wait_all(); fence_async_all(); }
-    __syncthreads();
+    if (bulk_pending) { bulk_wait_all(); fence_async_all(); }
+    __syncwarp();
     if (valid && !(a.tune & 2)) {
         TO *orow = net + grow * N;
-        int w = 0;
-        bool more = nw > 0;
-        unsigned ex = more ? mrow[0] : 0u;
-        for (;;) {
-            while (more && ex == 0) { ++w; more = w < nw; if (more) ex = mrow[w]; }
-            if (!more) break;
-            const int k = __ffs(ex) - 1;
-            ex &= ex - 1;
-            orow[j_of(w * 32 + k)] = idg;
+        if (!overflow) {
+            for (int c = 0; c < degl; ++c) orow[lst[c]] = idg;
+        } else if constexpr (PA32) {
+            for (int m = sub; m < a.NP2; m += LANES)
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * m + h;
+                    if (j < N && j != i && adj_only<EXACT>(xi, xe[j], a.R2)) orow[j] = idg;
+                }
+        } else {
+            for (int j = sub; j < N; j += LANES)
+                if (j != i && adj_only<EXACT>(xi, xe[j], a.R2)) orow[j] = idg;
         }
     }
 }

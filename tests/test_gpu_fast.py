@@ -82,3 +82,34 @@ def test_lanes_agree(precision):
         assert np.array_equal(nw, n0)
         assert normwise(v, v0) <= TOL[precision] and normwise(u, u0) <= TOL[precision]
         assert normwise(o, o0) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp64-exact", "fp64", "fp32"])
+@pytest.mark.parametrize("n,lanes", [(100, 0), (100, 1), (257, 4), (64, 2)])
+def test_dense_flock_overflows_candidate_lists(precision, n, lanes):
+    """A tight cluster (everybody within the radius of everybody): more candidates per row than the kernel's
+    candidate lists hold, so the all-pairs fallback path runs.  Same parity bars as everywhere else."""
+    from gym_flock_b200 import HostFlockBatch
+    from oracle import c_oracle
+    rs = np.random.RandomState(n)
+    e = 3
+    x0 = np.zeros((e, n, 4))
+    side = int(np.ceil(np.sqrt(n)))
+    grid = np.stack(np.meshgrid(np.arange(side), np.arange(side)), -1).reshape(-1, 2)[:n] * (0.8 / side)
+    x0[:, :, :2] = grid[None] + rs.uniform(-0.01, 0.01, size=(e, n, 2))
+    x0[:, :, 2:] = rs.uniform(-1, 1, size=(e, n, 2))
+    if precision == "fp64-exact" and lanes > 1:
+        pytest.skip("exact mode is one thread per row")
+    eng = HostFlockBatch(e, n, knn_obs=True, precision=precision, lanes=lanes)
+    eng.set_state(x0)
+    u = eng.controller(True)
+    for k in range(e):
+        h = c_oracle.helpers(x0[k])
+        assert h["adj"].sum(1).min() > 48
+        if precision == "fp64-exact":
+            assert np.array_equal(eng.values[k], h["values"]) and np.array_equal(eng.network[k], h["adj_mean"])
+            assert np.array_equal(u[k], c_oracle.controller(x0[k]))
+            assert np.array_equal(eng.obs[k], c_oracle.knn_obs(x0[k]))
+        else:
+            check_pass(x0[k], eng.values[k], eng.network[k], u[k], eng.reward[k], precision)
+    eng.close()
