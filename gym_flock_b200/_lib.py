@@ -13,7 +13,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libflock_b200.so")
+LIB_PATH = os.environ.get("FLOCK_LIB") or os.path.join(_PKG, "libflock_b200.so")
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in
             ("flock_abi.cu", "flock_env_kernel.cuh", "flock_common.cuh")] + \
            [os.path.join(_ROOT, "include", "flock_b200.h")]

@@ -75,8 +75,8 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
 
     // Rows per CTA window.  Small envs: flat windows over the E*nrows rows (every lane gets a row; a window stages
     // the few envs it touches).  Envs with at least a window of rows: row tiles per env.
-    int threads = (lanes > 1) ? 256 : (N < 256 ? 128 : 256);
-    if ((p->reserved & 0xff) > 0) threads = std::min(512, 32 * (p->reserved & 0xff));     // tuning override
+    int threads = 256;
+    if ((p->reserved & 0xff) > 0) threads = std::min(256, 32 * (p->reserved & 0xff));     // tuning override
     int RT = std::max(1, threads / lanes);
     const long long rows_total = (long long)E * nrows;
     if (rows_total < RT) RT = (int)rows_total;
@@ -87,16 +87,16 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     const bool pa32 = (tbytes == 4);                   // fp32 output mode filters on packed fp32 positions
     const int NP2 = (N + 1) / 2;
     const int nk_max = pa32 ? 2 * ((NP2 + lanes - 1) / lanes) : (N + lanes - 1) / lanes;
-    const int CAPL = std::min((nk_max + 1) & ~1, 48);   // candidate-list capacity per (row, lane); overflow -> all-pairs fallback
+    const int W = (nk_max + 31) / 32;
     flock::KArgs &k = pl.k;
     memset(&k, 0, sizeof(k));
     k.off_xs = 0;
     const size_t size_xs = (size_t)GMAX * N * 32;       // double4 per agent
     k.off_pf = align16(size_xs);
     const size_t size_pf = pa32 ? (size_t)GMAX * NP2 * 16 : 0;
-    k.off_lists = align16(k.off_pf + size_pf);
-    const size_t size_lists = (size_t)threads * (CAPL + 32) * 2;
-    k.off_stats = align16(k.off_lists + size_lists);
+    k.off_masks = align16(k.off_pf + size_pf);
+    const size_t size_lists = (size_t)threads * W * 4;
+    k.off_stats = align16(k.off_masks + size_lists);
     k.off_zero = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);
     pl.smem = (size_t)k.off_zero + flock::ZERO_BYTES;
     if (pl.smem > kMaxSmem)
@@ -112,7 +112,9 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
     }
     k.tune = p->reserved >> 8;
-    k.CAPL = CAPL; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
+    // small full rows: expand in the warp (coalesced stores); large rows: bulk zero-fill + scatter
+    k.out_mode = (lanes == 1 && nrows == N && (size_t)N * tbytes <= 2048 && !((p->reserved >> 8) & 16)) ? 1 : 0;
+    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
     pl.lanes = lanes; pl.threads = threads;
     pl.grid = grid;
     return FLOCK_OK;

@@ -29,6 +29,9 @@
 // batches still fill 148 SMs.
 #pragma once
 #include <type_traits>
+#ifndef FLOCK_MINB
+#define FLOCK_MINB 4   // resident 256-thread CTAs per SM the fast kernels are compiled for (register cap)
+#endif
 #include "flock_common.cuh"
 
 namespace flock {
@@ -48,13 +51,14 @@ struct KArgs {
     int GMAX;     // max envs a window touches (staging capacity)
     int row_lo, row_hi;
     int centralized;
-    int CAPL;     // candidate-list capacity per (row, lane) in entries (multiple of 2); lists hold CAPL + 32
+    int W;        // 32-bit candidate words per (row, lane)
     int NP2;      // pair slots per env in the packed fp32 position array: (N + 1) / 2
     double R, R2, dt, ascale;
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
-    unsigned off_xs, off_pf, off_lists, off_stats, off_zero;
-    int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter
+    unsigned off_xs, off_pf, off_masks, off_stats, off_zero;
+    int out_mode; // dense adjacency output: 0 = bulk zero-fill + scatter of the non-zeros; 1 = in-warp row expansion
+    int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
 };
 
 constexpr int ZERO_BYTES = 2048;   // shared zero block: source of the bulk (TMA) zero-fill of the dense adjacency
@@ -72,7 +76,7 @@ __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.as
 // shared-memory double accumulate (a handful per env and CTA; CAS loop is fine)
 __device__ __forceinline__ void smem_add(double *p, double v) { atomicAdd(p, v); }
 
-constexpr int STATS_PER_ENV = 4;   // ref vx, ref vy, S vx, S vy (sums of v - ref over the env)
+constexpr int STATS_PER_ENV = 4;   // sum vx, sum vy over the env (fp64), ready flag, pad
 constexpr int TOPK = KNN_K + 1;    // the diagonal (r2 = 0) rides along and is dropped at the end
 
 template <typename T> struct TopK {
@@ -150,19 +154,55 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
     return a;
 }
 
-// The adjacency decision alone, bit-identical to what refine_exact / refine_fast decide (overflow fallback).
-template <bool EXACT> __device__ __forceinline__ bool adj_only(const double4 xi, const double4 xj, const double R2) {
-    if constexpr (EXACT) {
-        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
-        return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < R2;
+// ---- in-warp expansion of the warp's rows of adj_mean (small rows) -----------------------------------------------
+// The warp's rows are consecutive rows of the [E*N, N] output.  A row is cut into nv = N/V groups of V elements
+// (16 bytes when V is maximal); a lane owns one group column (and, when rows are short, one of RPI rows handled per
+// iteration), so its mask word index and shift are loop invariants: per iteration one LDS, one SHFL (1/deg of the
+// row) and one coalesced streaming store.  No partial sectors, nothing to wait for.
+template <typename TO, int V>
+__device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, const int W, const int N, const int nrows,
+                                            const TO idg, const int lane) {
+    const int nv = N / V;                               // groups per row
+    const int passes = (nv + 31) >> 5;                  // > 1 when a row has more than 32 groups
+    const int rpi = (nv >= 32) ? 1 : 32 / nv;           // rows per iteration when rows are short
+    const int sr = (nv >= 32) ? 0 : lane / nv;          // this lane's sub-row within an iteration
+    const int cv0 = (nv >= 32) ? lane : lane - sr * nv; // this lane's group column (first pass)
+    const bool lane_on = (nv >= 32) || (sr < rpi);
+    auto emit = [&](const int rr, const int cv, const TO v) {
+        const int c = cv * V;                           // first column of the group
+        const unsigned bits = wmasks[(size_t)rr * W + (c >> 5)] >> (c & 31);
+        TO *dst = wout + (size_t)rr * N + c;
+        if constexpr (sizeof(TO) == 4 && V == 4) {
+            __stcs(reinterpret_cast<float4 *>(dst),
+                   make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
+        } else if constexpr (sizeof(TO) == 4 && V == 2) {
+            __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
+        } else if constexpr (sizeof(TO) == 8 && V == 2) {
+            __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
+        } else {
+            __stcs(dst, (bits & 1u) ? v : TO(0));
+        }
+    };
+    if (passes == 1) {                                  // the common case: a row fits one pass of the warp
+        const bool on = lane_on && cv0 < nv;
+#pragma unroll 4
+        for (int r = 0; r < nrows; r += rpi) {
+            const int rr = r + sr;
+            const TO v = __shfl_sync(0xffffffffu, idg, rr & 31);
+            if (on && rr < nrows) emit(rr, cv0, v);
+        }
     } else {
-        const double dx = xi.x - xj.x, dy = xi.y - xj.y;
-        return fma(dx, dx, dy * dy) < R2;
+        for (int r = 0; r < nrows; ++r) {
+            const TO v = __shfl_sync(0xffffffffu, idg, r);
+            for (int cv = lane; cv < nv; cv += 32) emit(r, cv, v);
+        }
     }
 }
 
+// Resident-CTA targets: the fast kernels are latency bound (divergent refine loops), so occupancy matters more than
+// registers: 256-thread bound, 6 CTAs (48 warps) per SM -> <= 40 registers.  EXACT keeps its registers.
 template <typename TO, int LANES, bool EXACT, bool KNN>
-__global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
+__global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
     constexpr bool PA32 = std::is_same<TO, float>::value;   // phase A on packed fp32 positions
     using TK = typename std::conditional<PA32, float, double>::type;
     static_assert(!EXACT || (!PA32 && LANES == 1), "EXACT is fp64, one thread per row");
@@ -170,7 +210,7 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double4 *xs = reinterpret_cast<double4 *>(smem + a.off_xs);
     float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf);       // (px_2m, px_2m+1, py_2m, py_2m+1) - env origin
-    unsigned short *lists = reinterpret_cast<unsigned short *>(smem + a.off_lists);
+    unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);
     double *stats = reinterpret_cast<double *>(smem + a.off_stats);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -189,65 +229,55 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     }
     const int e0 = r0 / nre;
     const int nenv = (r1 - 1) / nre - e0 + 1;
+    const float inv_n = 1.0f / (float)N, inv_nre = 1.0f / (float)nre;
     TO *net = reinterpret_cast<TO *>(a.network);
     TO *reward = reinterpret_cast<TO *>(a.reward);
 
-    // ---- zero block for the bulk fill, per-env accumulators ---------------------------------------------------
+    // ---- zero block for the bulk fill, stats flags ------------------------------------------------------------
     {
         float4 *zb = reinterpret_cast<float4 *>(smem + a.off_zero);
         for (int q = tid; q < ZERO_BYTES / 16; q += nthr) zb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (!EXACT) for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
         fence_async_smem();      // generic-proxy zeros -> visible to the async proxy (TMA) after the barrier
-        if constexpr (!EXACT) {
-            for (int q = tid; q < nenv * STATS_PER_ENV; q += nthr) stats[q] = 0.0;
-            __syncthreads();     // accumulators are added to below
-        }
     }
 
-    // ---- prologue: load, integrate, publish x', stage; gather per-env velocity sums -----------------------------
-    for (int ge = 0; ge < nenv; ++ge) {
-        const int env = e0 + ge;
-        const bool writer = (r0 <= env * nre) && (env * nre < r1);     // this CTA holds the env's first row
-        const double4 ref = ld_state(a.x_in + (size_t)env * N * 4);    // origin: agent 0 before integration
-        double sx = 0, sy = 0;
-        for (int j = tid; j < N; j += nthr) {
-            const size_t ga = (size_t)env * N + j;
+    // ---- prologue: load, integrate, publish x', stage (one flat loop over the agents of the staged envs) -----------
+    {
+        const int nag = nenv * N;
+        const size_t a0 = (size_t)e0 * N;
+        for (int idx = tid; idx < nag; idx += nthr) {
+            const size_t ga = a0 + idx;
             double4 x = ld_state(a.x_in + ga * 4);
             if (a.u_in) {
                 const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + ga);
                 x = integrate_exact(x, u, a.dt, a.ascale);
             }
-            if (a.x_out && writer) st_state(a.x_out + ga * 4, x);
-            xs[ge * N + j] = x;
-            if constexpr (!EXACT) { sx += x.z - ref.z; sy += x.w - ref.w; }
+            const int ge = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;     // exact: idx < 2^20
+            const int j = idx - ge * N;
+            // the CTA that owns agent j's row publishes its new state (every row is owned by exactly one CTA)
+            const int frj = (e0 + ge) * nre + (j - a.row_lo);
+            if (a.x_out && j >= a.row_lo && j < a.row_hi && frj >= r0 && frj < r1) st_state(a.x_out + ga * 4, x);
+            xs[idx] = x;
             if constexpr (PA32) {
-                float *p = reinterpret_cast<float *>(pf + (size_t)ge * a.NP2 + (j >> 1));
+                const double2 ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (a0 + (size_t)ge * N) * 4));
+                float *p = reinterpret_cast<float *>(pf + (size_t)ge * a.NP2 + (j >> 1));   // origin: agent 0 before the step
                 p[j & 1] = (float)(x.x - ref.x); p[2 + (j & 1)] = (float)(x.y - ref.y);
                 if ((N & 1) && j == N - 1) { p[1] = CUDART_INF_F; p[3] = CUDART_INF_F; }   // odd N: pad slot at infinity
-            }
-        }
-        if constexpr (!EXACT) {
-            if (tid - lane < N) {           // warps that staged agents of this env (uniform per warp)
-                sx = warp_sum(sx); sy = warp_sum(sy);
-                if (lane == 0) {
-                    double *st = stats + ge * STATS_PER_ENV;
-                    smem_add(st + 2, sx); smem_add(st + 3, sy);
-                    if (tid == 0) { st[0] = ref.z; st[1] = ref.w; }
-                }
             }
         }
     }
     __syncthreads();
     // ==== from here on warps are independent ======================================================================
 
-    // ---- rewards: the CTA holding an env's first row computes it, one warp per env -----------------------------------
-    if (reward) {
+    // ---- per-env velocity sums (alignment trick) and rewards: one warp per env, published through a flag ------------
+    {
         const int warp = tid >> 5, nwarps = nthr >> 5;
         for (int ge = warp; ge < nenv; ge += nwarps) {
             const int env = e0 + ge;
-            if (!((r0 <= env * nre) && (env * nre < r1))) continue;
+            const bool owner = reward && (r0 <= env * nre) && (env * nre < r1);     // CTA holding the env's first row
             const double4 *xe = xs + ge * N;
             if constexpr (EXACT) {
-                if (lane == 0) {            // NumPy's two-pass variance with sequential sums (:145-147)
+                if (lane == 0 && owner) {   // NumPy's two-pass variance with sequential sums (:145-147)
                     double sx = 0.0, sy = 0.0;
                     for (int j = 0; j < N; ++j) { sx = __dadd_rn(sx, xe[j].z); sy = __dadd_rn(sy, xe[j].w); }
                     const double mx = __ddiv_rn(sx, (double)N), my = __ddiv_rn(sy, (double)N);
@@ -259,16 +289,25 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
                     reward[env] = __dmul_rn(-1.0, __dadd_rn(__ddiv_rn(qx, (double)N), __ddiv_rn(qy, (double)N)));
                 }
             } else {
-                const double *st = stats + ge * STATS_PER_ENV;
-                const double invN = 1.0 / (double)N;
-                const double mx = fma(st[2], invN, st[0]), my = fma(st[3], invN, st[1]);
-                double qx = 0, qy = 0;
+                // sums about agent 0's velocity (a member of the flock: no cancellation problem)
+                const double rx = xe[0].z, ry = xe[0].w;
+                double sx = 0, sy = 0, qx = 0, qy = 0;
                 for (int j = lane; j < N; j += 32) {
-                    const double ex = xe[j].z - mx, ey = xe[j].w - my;
-                    qx = fma(ex, ex, qx); qy = fma(ey, ey, qy);
+                    const double ex = xe[j].z - rx, ey = xe[j].w - ry;
+                    sx += ex; sy += ey; qx = fma(ex, ex, qx); qy = fma(ey, ey, qy);
                 }
-                qx = warp_sum(qx + qy);
-                if (lane == 0) reward[env] = (TO)(-qx * invN);
+                sx = warp_sum(sx); sy = warp_sum(sy);
+                if (owner) {
+                    const double q = warp_sum(qx + qy);
+                    const double invN = 1.0 / (double)N;
+                    if (lane == 0) reward[env] = (TO)(-(q - (sx * sx + sy * sy) * invN) * invN);   // -(var x + var y)
+                }
+                if (lane == 0) {
+                    double *st = stats + ge * STATS_PER_ENV;
+                    st[0] = fma((double)N, rx, sx); st[1] = fma((double)N, ry, sy);      // sum_j v_j
+                    __threadfence_block();
+                    reinterpret_cast<volatile double *>(st)[2] = 1.0;                     // ready
+                }
             }
         }
     }
@@ -278,23 +317,20 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     const int fr = r0 + rl;                                 // flat row
     const bool valid = fr < r1;
     int g = 0;
-    if (valid && nenv > 1) {                                // env of this row, relative to e0 (exact float division:
-        const int lr = fr - e0 * nre;                       //   lr < RT + nre <= 2^17, see host plan)
-        g = (int)__fdividef((float)lr + 0.5f, (float)nre);
-    }
+    if (valid && nenv > 1) g = (int)(((float)(fr - e0 * nre) + 0.5f) * inv_nre);   // env of this row relative to e0 (exact)
     const int env = e0 + g;
     const int i = valid ? a.row_lo + (fr - env * nre) : 0;
     const bool cen = a.centralized != 0;
     const double4 *xe = xs + g * N;
     const double4 xi = xe[i];
-    unsigned short *lst = lists + (size_t)tid * (a.CAPL + 32);
+    unsigned *mrow = masks + (size_t)tid * a.W;
     const size_t grow = (size_t)env * N + i;                // global row (agent) index
 
     // ---- per-warp bulk zero-fill of the warp's rows of the dense adjacency ---------------------------------------
     // The rows of a warp are consecutive flat rows; with full rows (nre == N) they are ONE contiguous run in
     // memory, otherwise one run per env they belong to.  Lane l queues the l-th 2 KB piece of the run.
     bool bulk_pending = false;
-    if (net && !(a.tune & 1)) {
+    if (net && a.out_mode == 0 && !(a.tune & 1)) {
         const int wr0 = r0 + (tid - lane) / LANES;                           // first flat row of this warp
         const int wr1 = min(wr0 + 32 / LANES, r1);
         int s0 = wr0;
@@ -325,14 +361,15 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
     TopK<TK> top;
     if constexpr (KNN) top.init(i);
 
-    // ---- phase A: filter; candidates are appended to this lane's list (ascending j) ---------------------------------
-    //   fp32 packed : pair slot m = sub + LANES*t, agents j = 2m, 2m+1
+    // ---- phase A: filter ----------------------------------------------------------------------------------
+    // Each lane owns bit positions k = 0.. of its words; j_of(k) maps them to agents.
+    //   fp32 packed : pair slot m = sub + LANES*(k>>1), agent j = 2m + (k&1)
     //   fp64        : j = sub + LANES*k
-    unsigned short *lp = lst;                               // append pointer
-    unsigned short *const lend = lst + a.CAPL;              // soft capacity (a chunk may run 32 past it)
-    bool overflow = false;
+    int nk;                                                 // bit positions used by this lane
+    int cnt = 0;                                            // candidates found by this lane
     if constexpr (PA32) {
         const int nslots = valid ? (a.NP2 - sub + LANES - 1) / LANES : 0;
+        nk = 2 * nslots;
         const float4 *pe = pf + (size_t)g * a.NP2;
         const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
         const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
@@ -342,7 +379,9 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
         // |d(dx)| <= (2|p_i|inf + 3rc)*2^-24 and |d(r2)| <= 4 rc |d(dx)| + a few ulp(r2).
         const float tc = (float)a.thrC, rc = sqrtf(tc);
         const float thrA = tc * (1.0f + 2e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
-        for (int tbase = 0; tbase < nslots; tbase += 16) {
+        for (int w = 0; w * 16 < ((a.tune & 8) ? 0 : nslots); ++w) {
+            unsigned bits = 0;
+            const int tbase = w * 16;
             const int tend = min(16, nslots - tbase);
             auto body = [&](const int tt) {
                 const int m = sub + LANES * (tbase + tt);
@@ -350,8 +389,8 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
                 const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
                 const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
                 const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-                if (r2.x <= thrA) { *lp = (unsigned short)(2 * m); ++lp; }
-                if (r2.y <= thrA) { *lp = (unsigned short)(2 * m + 1); ++lp; }
+                bits |= (r2.x <= thrA) ? (1u << (2 * tt)) : 0u;
+                bits |= (r2.y <= thrA) ? (2u << (2 * tt)) : 0u;
                 if constexpr (KNN) { top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1); }
             };
             if (tend == 16) {
@@ -360,12 +399,15 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
             } else {
                 for (int tt = 0; tt < tend; ++tt) body(tt);
             }
-            if (lp > lend) { overflow = true; lp = lst; }   // too dense for the list: fall back to all pairs
+            mrow[w] = bits;
+            cnt += __popc(bits);
         }
     } else {
-        const int nk = valid ? (N - sub + LANES - 1) / LANES : 0;
+        nk = valid ? (N - sub + LANES - 1) / LANES : 0;
         const double thrC = a.thrC;
-        for (int kbase = 0; kbase < nk; kbase += 32) {
+        for (int w = 0; w * 32 < nk; ++w) {
+            unsigned bits = 0;
+            const int kbase = w * 32;
             const int kend = min(32, nk - kbase);
             auto body = [&](const int kk) {
                 const int j = sub + LANES * (kbase + kk);
@@ -385,7 +427,7 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
                     r2 = fma(dx, dx, dy * dy);
                     c = r2 <= thrC;
                 }
-                if (c) { *lp = (unsigned short)j; ++lp; }
+                bits |= c ? (1u << kk) : 0u;
                 if constexpr (KNN) top.insert(r2, j);
             };
             if (kend == 32) {
@@ -394,75 +436,18 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
             } else {
                 for (int kk = 0; kk < kend; ++kk) body(kk);
             }
-            if (lp > lend) { overflow = true; lp = lst; }
+            mrow[w] = bits;
+            cnt += __popc(bits);
         }
     }
-
-    // ---- phase B: refine the candidates in fp64, ascending j per lane; neighbours are compacted in place ------------
-    int deg = 0;
-    auto refine = [&](const int j) -> bool {
-        const double4 xj = xe[j];
-        if constexpr (EXACT) return refine_exact(xi, xj, a.R, a.R2, cen, A);
-        else return refine_fast(xi, xj, a.R2, a.Rm, A);
+    const int nw = (nk + 31) >> 5;
+    auto j_of = [&](const int k) -> int {
+        if constexpr (PA32) return 2 * (sub + LANES * (k >> 1)) + (k & 1);
+        else return sub + LANES * k;
     };
-    if (!overflow) {
-        const int ncand = (int)(lp - lst);
-        for (int c = 0; c < ncand; ++c) {
-            const int j = lst[c];
-            if (j != i && refine(j)) { lst[deg] = (unsigned short)j; ++deg; }   // diagonal: r2 = +inf in the reference (:115)
-        }
-    } else if (valid) {                                     // rare: more candidates than the list holds
-        if constexpr (PA32) {
-            for (int m = sub; m < a.NP2; m += LANES)
-                for (int h = 0; h < 2; ++h) { const int j = 2 * m + h; if (j < N && j != i && refine(j)) ++deg; }
-        } else {
-            for (int j = sub; j < N; j += LANES) if (j != i && refine(j)) ++deg;
-        }
-    }
-    int degl = deg;                                         // neighbours found by this lane
 
-    // ---- reduce across the LANES threads of a row ----------------------------------------------------------
-    if constexpr (LANES > 1) {
-#pragma unroll
-        for (int m = LANES / 2; m > 0; m >>= 1) {
-            A.f0 += shfl_xor(A.f0, m); A.f1 += shfl_xor(A.f1, m); A.f2 += shfl_xor(A.f2, m);
-            A.f3 += shfl_xor(A.f3, m); A.f4 += shfl_xor(A.f4, m); A.f5 += shfl_xor(A.f5, m);
-            A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
-            deg += shfl_xor(deg, m);
-        }
-    }
-
-    // ---- row epilogue: features, action, 1/deg ---------------------------------------------------------------
-    TO idg;
-    if constexpr (EXACT) idg = __ddiv_rn(1.0, (double)max(deg, 1));               // :121-122
-    else if constexpr (PA32) idg = __frcp_rn((float)max(deg, 1));
-    else idg = Tr<double>::rcp((double)max(deg, 1));
-    if (valid && sub == 0) {
-        if (a.values) {
-            TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
-            v[0] = (TO)A.f0; v[1] = (TO)A.f1; v[2] = (TO)A.f2; v[3] = (TO)A.f3; v[4] = (TO)A.f4; v[5] = (TO)A.f5;
-        }
-        if (a.u_next) {
-            double ux, uy;
-            if constexpr (EXACT) {
-                ux = __dsub_rn(-A.gx, A.s0);             // (-S.gx) - S.dvx      flocking_relative.py:209
-                uy = __dsub_rn(-A.s1, A.gy);             // (-S.dvy) - S.gy
-                ux = fmin(fmax(ux, -10.0), 10.0); uy = fmin(fmax(uy, -10.0), 10.0);   // :210
-                ux = __ddiv_rn(ux, a.ascale); uy = __ddiv_rn(uy, a.ascale);           // :211
-            } else {
-                const double *st = stats + g * STATS_PER_ENV;
-                // centralized: sum_j (v_i - v_j) = N*(v_i - ref) - sum_j (v_j - ref); decentralized: masked sum = f0/f3
-                const double sdx = cen ? fma((double)N, xi.z - st[0], -st[2]) : A.f0;
-                const double sdy = cen ? fma((double)N, xi.w - st[1], -st[3]) : A.f3;
-                const double ia = Tr<double>::rcp(a.ascale);     // 1/10 to ~1 ulp; one extra rounding vs a true divide
-                ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * ia;
-                uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * ia;
-            }
-            reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
-        }
-    }
-
-    // ---- kNN observation: merge the LANES partial lists, drop the diagonal, obs[i, 4m:4m+4] = x_i - x_nbr(m) ----
+    // ---- kNN observation (independent of phase B): merge the LANES partial lists, drop the diagonal,
+    //      obs[i, 4m:4m+4] = x_i - x_nbr(m)                                                 flocking.py:20-24
     if constexpr (KNN) {
         int nb[TOPK];
 #pragma unroll
@@ -502,25 +487,114 @@ __global__ void __launch_bounds__(512) flock_env_kernel(const KArgs a) {
         }
     }
 
-    // ---- scatter the non-zero adj_mean entries (1/deg) into the warp's zero-filled rows --------------------------
-    // Every lane that queued bulk zero stores waits for them and orders them (async proxy) before the generic-proxy
-    // stores below; __syncwarp then releases the warp.  A warp only ever touches its own rows.
+    // ---- phase B: refine the candidates in fp64, ascending j per lane; rewrite the words with the exact bits ----
+    // One flat loop per lane; the advance to the next word is straight-line code inside the loop body, so a warp
+    // iterates ~max-over-lanes(total candidates) times.
+    int deg = 0;
+    if (!(a.tune & 4)) {
+        int w = 0;
+        unsigned cand = nw > 0 ? mrow[0] : 0u, ex = 0;
+        for (int c = 0; c < cnt; ++c) {                     // counted loop: cnt candidates are known to exist
+            while (cand == 0) {                             // word exhausted: publish its exact bits, fetch the next
+                mrow[w] = ex; ex = 0;
+                ++w;
+                cand = mrow[w];
+            }
+            const int k = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int j = j_of(w * 32 + k);
+            if (j != i) {                                   // diagonal: r2 = +inf in the reference (:115)
+                const double4 xj = xe[j];
+                bool adj;
+                if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
+                else adj = refine_fast(xi, xj, a.R2, a.Rm, A);
+                if (adj) { ex |= 1u << k; ++deg; }
+            }
+        }
+        if (nw > 0) mrow[w] = ex;                           // words after w held no candidates: already zero
+    }
+
+    // ---- reduce across the LANES threads of a row ----------------------------------------------------------
+    if constexpr (LANES > 1) {
+#pragma unroll
+        for (int m = LANES / 2; m > 0; m >>= 1) {
+            A.f0 += shfl_xor(A.f0, m); A.f1 += shfl_xor(A.f1, m); A.f2 += shfl_xor(A.f2, m);
+            A.f3 += shfl_xor(A.f3, m); A.f4 += shfl_xor(A.f4, m); A.f5 += shfl_xor(A.f5, m);
+            A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
+            deg += shfl_xor(deg, m);
+        }
+    }
+
+    // ---- row epilogue: features, action, 1/deg ---------------------------------------------------------------
+    TO idg;
+    if constexpr (EXACT) idg = __ddiv_rn(1.0, (double)max(deg, 1));               // :121-122
+    else if constexpr (PA32) idg = __frcp_rn((float)max(deg, 1));
+    else idg = Tr<double>::rcp((double)max(deg, 1));
+    if (valid && sub == 0) {
+        if (a.values) {
+            TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
+            v[0] = (TO)A.f0; v[1] = (TO)A.f1; v[2] = (TO)A.f2; v[3] = (TO)A.f3; v[4] = (TO)A.f4; v[5] = (TO)A.f5;
+        }
+        if (a.u_next) {
+            double ux, uy;
+            if constexpr (EXACT) {
+                ux = __dsub_rn(-A.gx, A.s0);             // (-S.gx) - S.dvx      flocking_relative.py:209
+                uy = __dsub_rn(-A.s1, A.gy);             // (-S.dvy) - S.gy
+                ux = fmin(fmax(ux, -10.0), 10.0); uy = fmin(fmax(uy, -10.0), 10.0);   // :210
+                ux = __ddiv_rn(ux, a.ascale); uy = __ddiv_rn(uy, a.ascale);           // :211
+            } else {
+                double sdx = A.f0, sdy = A.f3;           // decentralized: the masked sums (:205-206)
+                if (cen) {                               // centralized: sum_j (v_i - v_j) = N*v_i - sum_j v_j, about agent 0
+                    const volatile double *st = stats + g * STATS_PER_ENV;
+                    while (st[2] == 0.0) { }             // published long ago by the stats warp (never waits on us)
+                    __threadfence_block();
+                    const double rx = xe[0].z, ry = xe[0].w;
+                    sdx = fma((double)N, xi.z - rx, -(st[0] - (double)N * rx));
+                    sdy = fma((double)N, xi.w - ry, -(st[1] - (double)N * ry));
+                }
+                const double ia = Tr<double>::rcp(a.ascale);     // 1/10 to ~1 ulp; one extra rounding vs a true divide
+                ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * ia;
+                uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * ia;
+            }
+            reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
+        }
+    }
+
+    // ---- dense adj_mean rows ---------------------------------------------------------------------------------------
     if (net == nullptr) return;
-    if (bulk_pending) { bulk_wait_all(); fence_async_all(); }
+    if (a.out_mode == 1) {
+        // small rows: expand the warp's 32 rows from their exact bit masks (LANES == 1, full rows; host guarantees it)
+        if constexpr (LANES == 1) {
+            __syncwarp();                                    // the lanes' mask words (shared memory) are complete
+            const int wr0 = r0 + (tid - lane);               // first flat row of this warp == its global row (nre == N)
+            const int nrows = min(32, r1 - wr0);
+            if (nrows > 0 && !(a.tune & 2)) {
+                TO *wout = net + (size_t)wr0 * N;
+                const unsigned *wm = masks + (size_t)(tid - lane) * a.W;
+                constexpr int VMAX = 16 / (int)sizeof(TO);
+                if (N % VMAX == 0) expand_rows<TO, VMAX>(wout, wm, a.W, N, nrows, idg, lane);
+                else if (VMAX == 4 && N % 2 == 0) expand_rows<TO, 2>(wout, wm, a.W, N, nrows, idg, lane);
+                else expand_rows<TO, 1>(wout, wm, a.W, N, nrows, idg, lane);
+            }
+        }
+        return;
+    }
+    // large rows: scatter the few non-zero entries (1/deg) into the warp's zero-filled rows.  Every lane that queued
+    // bulk zero stores waits for them and orders them (async proxy) before the generic-proxy stores below;
+    // __syncwarp then releases the warp.  A warp only ever touches its own rows.
+    if (bulk_pending && !(a.tune & 32)) { bulk_wait_all(); fence_async_all(); }
     __syncwarp();
     if (valid && !(a.tune & 2)) {
         TO *orow = net + grow * N;
-        if (!overflow) {
-            for (int c = 0; c < degl; ++c) orow[lst[c]] = idg;
-        } else if constexpr (PA32) {
-            for (int m = sub; m < a.NP2; m += LANES)
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 2 * m + h;
-                    if (j < N && j != i && adj_only<EXACT>(xi, xe[j], a.R2)) orow[j] = idg;
-                }
-        } else {
-            for (int j = sub; j < N; j += LANES)
-                if (j != i && adj_only<EXACT>(xi, xe[j], a.R2)) orow[j] = idg;
+        int w = 0;
+        unsigned ex = nw > 0 ? mrow[0] : 0u;
+        while (w < nw) {
+            if (ex == 0) { ++w; ex = (w < nw) ? mrow[w] : 0u; }
+            if (ex != 0) {
+                const int k = __ffs(ex) - 1;
+                ex &= ex - 1;
+                orow[j_of(w * 32 + k)] = idg;
+            }
         }
     }
 }
