@@ -184,12 +184,32 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, co
         }
     };
     if (passes == 1) {                                  // the common case: a row fits one pass of the warp
+        // loop invariants per lane: mask word / shift of its group column; pointers advance by rpi rows per iteration
         const bool on = lane_on && cv0 < nv;
+        const int c = cv0 * V;
+        const int sh = c & 31;
+        const unsigned *mp = wmasks + sr * W + (c >> 5);
+        TO *dst = wout + (size_t)sr * N + c;
+        const int mstep = rpi * W;
+        const size_t dstep = (size_t)rpi * N;
+        const int last = nrows - sr;                    // this lane stores while r < last
 #pragma unroll 4
         for (int r = 0; r < nrows; r += rpi) {
-            const int rr = r + sr;
-            const TO v = __shfl_sync(0xffffffffu, idg, rr & 31);
-            if (on && rr < nrows) emit(rr, cv0, v);
+            const TO v = __shfl_sync(0xffffffffu, idg, (r + sr) & 31);
+            if (on && r < last) {
+                const unsigned bits = *mp >> sh;
+                if constexpr (sizeof(TO) == 4 && V == 4) {
+                    __stcs(reinterpret_cast<float4 *>(dst),
+                           make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
+                } else if constexpr (sizeof(TO) == 4 && V == 2) {
+                    __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
+                } else if constexpr (sizeof(TO) == 8 && V == 2) {
+                    __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
+                } else {
+                    __stcs(dst, (bits & 1u) ? v : TO(0));
+                }
+            }
+            mp += mstep; dst += dstep;
         }
     } else {
         for (int r = 0; r < nrows; ++r) {
@@ -492,6 +512,13 @@ __global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(
     // iterates ~max-over-lanes(total candidates) times.
     int deg = 0;
     if (!(a.tune & 4)) {
+        // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
+        {
+            int kd = -1;
+            if constexpr (PA32) { if (valid && ((i >> 1) % LANES) == sub) kd = 2 * ((i >> 1) / LANES) + (i & 1); }
+            else { if (valid && (i % LANES) == sub) kd = i / LANES; }
+            if (kd >= 0) { mrow[kd >> 5] &= ~(1u << (kd & 31)); --cnt; }
+        }
         int w = 0;
         unsigned cand = nw > 0 ? mrow[0] : 0u, ex = 0;
         for (int c = 0; c < cnt; ++c) {                     // counted loop: cnt candidates are known to exist
@@ -502,14 +529,11 @@ __global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(
             }
             const int k = __ffs(cand) - 1;
             cand &= cand - 1;
-            const int j = j_of(w * 32 + k);
-            if (j != i) {                                   // diagonal: r2 = +inf in the reference (:115)
-                const double4 xj = xe[j];
-                bool adj;
-                if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
-                else adj = refine_fast(xi, xj, a.R2, a.Rm, A);
-                if (adj) { ex |= 1u << k; ++deg; }
-            }
+            const double4 xj = xe[j_of(w * 32 + k)];
+            bool adj;
+            if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
+            else adj = refine_fast(xi, xj, a.R2, a.Rm, A);
+            if (adj) { ex |= 1u << k; ++deg; }
         }
         if (nw > 0) mrow[w] = ex;                           // words after w held no candidates: already zero
     }
