@@ -114,7 +114,7 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     k.tune = p->reserved >> 8;
     // small full rows: expand in the warp (coalesced stores); large rows: bulk zero-fill + scatter
     k.out_mode = (lanes == 1 && nrows == N && (size_t)N * tbytes <= 2048 && !((p->reserved >> 8) & 16)) ? 1 : 0;
-    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar;
+    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar;
     pl.lanes = lanes; pl.threads = threads;
     pl.grid = grid;
     return FLOCK_OK;

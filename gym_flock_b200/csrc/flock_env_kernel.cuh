@@ -54,6 +54,7 @@ struct KArgs {
     int W;        // 32-bit candidate words per (row, lane)
     int NP2;      // pair slots per env in the packed fp32 position array: (N + 1) / 2
     double R, R2, dt, ascale;
+    double inv_ascale;   // 1/ascale (fast modes multiply; EXACT divides)
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
     unsigned off_xs, off_pf, off_masks, off_stats, off_zero;
@@ -183,7 +184,31 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, co
             __stcs(dst, (bits & 1u) ? v : TO(0));
         }
     };
-    if (passes == 1) {                                  // the common case: a row fits one pass of the warp
+    auto put = [&](TO *dst, const unsigned bits, const TO v) {
+        if constexpr (sizeof(TO) == 4 && V == 4) {
+            __stcs(reinterpret_cast<float4 *>(dst),
+                   make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
+        } else if constexpr (sizeof(TO) == 4 && V == 2) {
+            __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
+        } else if constexpr (sizeof(TO) == 8 && V == 2) {
+            __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
+        } else {
+            __stcs(dst, (bits & 1u) ? v : TO(0));
+        }
+    };
+    if (passes == 1 && rpi == 1 && nrows == 32) {       // a full warp of rows, one row per iteration: fixed trip count
+        const bool on = lane < nv;
+        const int c = on ? lane * V : 0;
+        const int sh = c & 31;
+        const unsigned *mp = wmasks + (c >> 5);
+        TO *dst = wout + c;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const TO v = __shfl_sync(0xffffffffu, idg, r);     // 1/deg of row r (held by lane r)
+            if (on) put(dst, *mp >> sh, v);
+            mp += W; dst += N;
+        }
+    } else if (passes == 1) {                           // short rows (several per iteration) or a partial warp
         // loop invariants per lane: mask word / shift of its group column; pointers advance by rpi rows per iteration
         const bool on = lane_on && cv0 < nv;
         const int c = cv0 * V;
@@ -193,22 +218,9 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, co
         const int mstep = rpi * W;
         const size_t dstep = (size_t)rpi * N;
         const int last = nrows - sr;                    // this lane stores while r < last
-#pragma unroll 4
         for (int r = 0; r < nrows; r += rpi) {
             const TO v = __shfl_sync(0xffffffffu, idg, (r + sr) & 31);
-            if (on && r < last) {
-                const unsigned bits = *mp >> sh;
-                if constexpr (sizeof(TO) == 4 && V == 4) {
-                    __stcs(reinterpret_cast<float4 *>(dst),
-                           make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
-                } else if constexpr (sizeof(TO) == 4 && V == 2) {
-                    __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
-                } else if constexpr (sizeof(TO) == 8 && V == 2) {
-                    __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
-                } else {
-                    __stcs(dst, (bits & 1u) ? v : TO(0));
-                }
-            }
+            if (on && r < last) put(dst, *mp >> sh, v);
             mp += mstep; dst += dstep;
         }
     } else {
@@ -576,7 +588,7 @@ __global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(
                     sdx = fma((double)N, xi.z - rx, -(st[0] - (double)N * rx));
                     sdy = fma((double)N, xi.w - ry, -(st[1] - (double)N * ry));
                 }
-                const double ia = Tr<double>::rcp(a.ascale);     // 1/10 to ~1 ulp; one extra rounding vs a true divide
+                const double ia = a.inv_ascale;                  // one extra rounding vs a true divide
                 ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * ia;
                 uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * ia;
             }
