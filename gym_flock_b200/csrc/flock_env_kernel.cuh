@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(
             }
             const int ge = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;     // exact: idx < 2^20
             const int j = idx - ge * N;
-            // the CTA that owns agent j's row publishes its new state (every row is owned by exactly one CTA)
-            const int frj = (e0 + ge) * nre + (j - a.row_lo);
-            if (a.x_out && j >= a.row_lo && j < a.row_hi && frj >= r0 && frj < r1) st_state(a.x_out + ga * 4, x);
+            // every agent's new state is published exactly once: by the CTA that owns local row (j mod rows-per-env)
+            // of its env (with full rows that is simply the CTA owning agent j's row)
+            const int frj = (e0 + ge) * nre + ((nre == N) ? j : j % nre);
+            if (a.x_out && frj >= r0 && frj < r1) st_state(a.x_out + ga * 4, x);
             xs[idx] = x;
             if constexpr (PA32) {
                 const double2 ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (a0 + (size_t)ge * N) * 4));

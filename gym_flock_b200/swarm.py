@@ -1,0 +1,136 @@
+"""SwarmEnv: ONE giant flock whose rows (agents i) are sharded over the ranks of a torch.distributed group.
+
+Protocol per step: every rank holds the full state x[N,4] and the full
+action u[N,2]; rank r runs the fused step kernel for rows [r*N/R, (r+1)*N/R) only (the kernel integrates all N agents
+into its staging copy, but computes features / adjacency rows / kNN obs / the next action for its rows only) and the
+ranks all-gather the new actions (N*2 float64: half the bytes of gathering x) so that every rank can integrate all rows
+at the next step.  No other data-path collective.  Row arithmetic never depends on the shard: world sizes 1 and 8
+produce identical bits.
+
+Outputs stay row-sharded: values[rows,6] / obs[rows,28], network[rows,N], and the (replicated) scalar reward.
+
+`row_backend` lets tests replace the CUDA launch by a CPU stand-in to exercise the sharding / all-gather logic under
+gloo without a GPU; the product path (row_backend=None) is the CUDA kernel and raises without it.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+_IDS = {"FlockingRelative-v0": False, "Flocking-v0": True}
+_PREC = {"fp64-exact": (torch.float64, True), "fp64": (torch.float64, False), "fp32": (torch.float32, False)}
+
+
+def shard_rows(n_agents: int, world: int, rank: int) -> tuple:
+    """Equal contiguous row blocks (the in-place all-gather needs equal shards)."""
+    if n_agents % world:
+        raise ValueError(f"n_agents={n_agents} must be divisible by the world size {world}")
+    per = n_agents // world
+    return rank * per, (rank + 1) * per
+
+
+class SwarmEnv:
+    def __init__(self, env_id: str = "Flocking-v0", n_agents: int = 65536, precision: str = "fp32",
+                 device=None, group=None, comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
+                 adjacency_mode: str = "dense", row_backend=None, lanes: int = 0):
+        if env_id not in _IDS:
+            raise KeyError(env_id)
+        self.knn = _IDS[env_id]
+        self.N = int(n_agents)
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.lo, self.hi = shard_rows(self.N, self.world, self.rank)
+        self.dtype, self.exact = _PREC[precision]
+        self.precision = precision
+        self.centralized, self.comm_radius, self.dt = bool(centralized), float(comm_radius), float(dt)
+        self.row_backend = row_backend
+        self.adjacency_mode = adjacency_mode
+        if row_backend is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("SwarmEnv needs a CUDA device (no CPU fallback); tests may inject row_backend")
+            from . import _lib
+            self._lib = _lib
+            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            self._params = _lib.make_params(1, self.N, comm_radius=comm_radius, dt=dt, centralized=centralized,
+                                            exact=self.exact, knn_obs=self.knn, rows=(self.lo, self.hi), lanes=lanes)
+            self._fn = _lib.lib().flock_step_f64 if self.dtype == torch.float64 else _lib.lib().flock_step_f32
+        else:
+            self.device = torch.device("cpu")
+        n, rows, dev, f64 = self.N, self.hi - self.lo, self.device, torch.float64
+        self._x = [torch.zeros(n, 4, dtype=f64, device=dev) for _ in range(2)]
+        self._u = [torch.zeros(n, 2, dtype=f64, device=dev) for _ in range(2)]
+        self._cur = 0
+        self.values = torch.zeros(rows, 6, dtype=self.dtype, device=dev)
+        self.network = torch.zeros(rows, n, dtype=self.dtype, device=dev) if adjacency_mode == "dense" else None
+        self.obs = torch.zeros(rows, 28, dtype=self.dtype, device=dev) if self.knn else None
+        self.reward = torch.zeros(1, dtype=self.dtype, device=dev)
+
+    # ---- plumbing ----------------------------------------------------------------------------------------------
+    @property
+    def x(self) -> torch.Tensor:
+        return self._x[self._cur]
+
+    @property
+    def u(self) -> torch.Tensor:
+        """controller() action for the current state, all N rows (gathered)."""
+        return self._u[self._cur]
+
+    def _shifted(self, t, row_elems):
+        """Device pointer of a shard-sized buffer shifted back by row_lo rows (the kernel indexes by global row)."""
+        if t is None:
+            return None
+        return ctypes.c_void_p(t.data_ptr() - self.lo * row_elems * t.element_size())
+
+    def _launch(self, x_in, u_in, x_out, u_next):
+        if self.row_backend is not None:
+            out = self.row_backend(x_in.numpy(), None if u_in is None else u_in.numpy(), self.lo, self.hi,
+                                   dict(comm_radius=self.comm_radius, dt=self.dt, centralized=self.centralized, knn=self.knn))
+            if x_out is not None:
+                x_out.copy_(torch.from_numpy(out["x"]))
+            u_next[self.lo:self.hi].copy_(torch.from_numpy(out["u_rows"]))
+            self.values.copy_(torch.from_numpy(out["values_rows"]).to(self.dtype))
+            if self.network is not None:
+                self.network.copy_(torch.from_numpy(out["network_rows"]).to(self.dtype))
+            if self.obs is not None:
+                self.obs.copy_(torch.from_numpy(out["obs_rows"]).to(self.dtype))
+            self.reward.fill_(float(out["reward"]))
+            return
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            self._lib.check(self._fn(ctypes.byref(self._params), p(x_in), p(u_in), p(x_out),
+                                     self._shifted(self.values, 6), self._shifted(self.network, self.N), p(self.reward),
+                                     p(u_next), self._shifted(self.obs, 28),
+                                     ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def _gather_actions(self, u_full):
+        """In-place all-gather of the rows each rank just computed (equal shards, rank order = row order)."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(u_full, u_full[self.lo:self.hi].clone(), group=self.group)
+
+    def _observation(self):
+        return (self.obs if self.knn else self.values), self.network
+
+    # ---- API -----------------------------------------------------------------------------------------------------
+    def reset(self, x0):
+        """x0[N,4]: the same full state on every rank."""
+        x0 = torch.as_tensor(np.asarray(x0) if not torch.is_tensor(x0) else x0, dtype=torch.float64)
+        self.x.copy_(x0.reshape(self.N, 4))
+        self._launch(self.x, None, None, self._u[self._cur])
+        self._gather_actions(self._u[self._cur])
+        return self._observation()
+
+    def step(self, u=None):
+        """u[N,2] full action (same on every rank) or None = the gathered controller action."""
+        u_in = self.u if u is None else torch.as_tensor(u, dtype=torch.float64, device=self.device).reshape(self.N, 2)
+        nxt = self._cur ^ 1
+        if u_in.data_ptr() == self._u[nxt].data_ptr():
+            u_in = u_in.clone()
+        self._launch(self.x, u_in, self._x[nxt], self._u[nxt])
+        self._cur = nxt
+        self._gather_actions(self._u[nxt])
+        return self._observation(), self.reward, False, {}

@@ -59,7 +59,9 @@ typedef struct FlockParams {
     int32_t flags;          /* FLOCK_* */
     int32_t knn;            /* neighbours in obs; 7 (flocking.py:9); only with FLOCK_KNN_OBS */
     int32_t row_lo;         /* swarm sharding: this call computes rows [row_lo,row_hi) of every env; */
-    int32_t row_hi;         /*   0,0 (or 0,N) = all rows.  x_in / u_in are always full [E][N][*]. */
+    int32_t row_hi;         /*   0,0 (or 0,N) = all rows.  x_in / u_in / x_out are always full [E][N][*].  Outputs are
+                             *   addressed by GLOBAL row but only rows [row_lo,row_hi) are ever touched, so a caller
+                             *   may pass shard-sized buffers shifted back by row_lo rows. */
     int32_t lanes;          /* threads cooperating on one row (power of two <= 32); 0 = choose */
     int32_t reserved;
 } FlockParams;
@@ -73,7 +75,7 @@ void        flock_host_free(void *p);
 
 /* One fused step on device buffers.
  *   x' = u_in ? integrate(x_in, u_in) : x_in          (flocking_relative.py:96-105)
- *   x_out (if non-NULL) <- x'   (all rows of every env; x_out may NOT alias x_in)
+ *   x_out (if non-NULL) <- x'   (ALL rows of every env, also in row-sharded calls; x_out may NOT alias x_in)
  *   then ONE pass over the ordered pairs of x' produces, for rows [row_lo,row_hi):
  *     values [E][N][6]      state_values   (:124-129)           (nullable)
  *     network[E][N][N]      adj_mat_mean   (:117-122,131-132)   (nullable: skip the dense write)
