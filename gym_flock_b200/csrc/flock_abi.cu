@@ -12,6 +12,7 @@
 
 #include "../../include/flock_b200.h"
 #include "flock_env_kernel.cuh"
+#include "flock_swarm_kernel.cuh"
 
 namespace {
 
@@ -201,6 +202,101 @@ int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, doub
     return FLOCK_OK;
 }
 
+
+// ---- large swarms: prep kernel + streaming row kernel (flock_swarm_kernel.cuh) --------------------------------------
+struct SwarmLayout { size_t off_pf, off_partials, off_totals, off_counters, bytes; int NP2, PB; };
+
+SwarmLayout swarm_layout(int E, int N) {
+    SwarmLayout L;
+    L.NP2 = (N + 1) / 2;
+    L.PB = (N + flock::PREP_THREADS - 1) / flock::PREP_THREADS;
+    L.off_pf = 0;
+    L.off_partials = ((size_t)E * L.NP2 * 16 + 255) & ~(size_t)255;
+    L.off_totals = L.off_partials + (((size_t)E * L.PB * 32 + 255) & ~(size_t)255);
+    L.off_counters = L.off_totals + (((size_t)E * 64 + 255) & ~(size_t)255);
+    L.bytes = L.off_counters + (((size_t)E * 4 + 255) & ~(size_t)255);
+    return L;
+}
+
+template <typename TO, int LANES>
+int swarm_launch(const flock::SArgs &a, bool knn, dim3 grid, size_t smem, cudaStream_t st) {
+    auto k0 = flock::flock_swarm_kernel<TO, LANES, false>;
+    auto k1 = flock::flock_swarm_kernel<TO, LANES, true>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        configured_dev = dev;
+    }
+    if (knn) k1<<<grid, 256, smem, st>>>(a); else k0<<<grid, 256, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}
+
+template <typename T>
+int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
+                    T *reward, double *u_next, T *obs, void *scratch, size_t scratch_bytes, void *stream) {
+    if (!p) return fail(FLOCK_EINVAL, "params is NULL");
+    const int E = p->n_envs, N = p->n_agents;
+    if (E < 1 || N < 2) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d", E, N);
+    if (p->flags & FLOCK_EXACT_ORDER)
+        return fail(FLOCK_EUNSUPPORTED, "FLOCK_EXACT_ORDER is offered by the env-resident path only (flock_step_f64)");
+    if ((p->flags & FLOCK_KNN_OBS) && p->knn != flock::KNN_K) return fail(FLOCK_EUNSUPPORTED, "knn=%d", p->knn);
+    int row_lo = p->row_lo, row_hi = p->row_hi;
+    if (row_lo == 0 && row_hi == 0) row_hi = N;
+    if (row_lo < 0 || row_hi > N || row_lo >= row_hi) return fail(FLOCK_EINVAL, "bad row range [%d,%d)", row_lo, row_hi);
+    if (!x_in || !x_out || !scratch) return fail(FLOCK_EINVAL, "x_in, x_out and scratch are required");
+    if (x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
+    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values) || misaligned(network) ||
+        misaligned(u_next) || misaligned(obs) || (reinterpret_cast<uintptr_t>(scratch) & 255u))
+        return fail(FLOCK_EALIGN, "device buffers must be 16-byte aligned (scratch: 256)");
+    const SwarmLayout L = swarm_layout(E, N);
+    if (scratch_bytes < L.bytes) return fail(FLOCK_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, L.bytes);
+    int lanes = p->lanes > 0 ? p->lanes : 32;
+    if (lanes != 8 && lanes != 16 && lanes != 32) return fail(FLOCK_EINVAL, "swarm path: lanes must be 8, 16 or 32");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char *sc = reinterpret_cast<char *>(scratch);
+
+    flock::SArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_in = x_in; a.u_in = u_in; a.x_cur = x_out; a.u_next = u_next;
+    a.values = values; a.network = network; a.reward = reward; a.obs = (p->flags & FLOCK_KNN_OBS) ? obs : nullptr;
+    a.pf = reinterpret_cast<float4 *>(sc + L.off_pf);
+    a.partials = reinterpret_cast<double *>(sc + L.off_partials);
+    a.totals = reinterpret_cast<double *>(sc + L.off_totals);
+    a.counters = reinterpret_cast<unsigned *>(sc + L.off_counters);
+    a.E = E; a.N = N; a.NP2 = L.NP2; a.PB = L.PB; a.row_lo = row_lo; a.row_hi = row_hi;
+    a.RT = 256 / lanes;
+    a.TS = 2048;
+    a.WT = (2 * ((a.TS + lanes - 1) / lanes) + 31) / 32;
+    a.CAP = 256;
+    a.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
+    a.R = p->comm_radius; a.R2 = p->comm_radius2; a.thrC = std::max(a.R, a.R2);
+    a.Rm = (a.centralized || a.R2 > a.R) ? a.R : std::nextafter(a.R2, -1.0);
+    a.dt = p->dt; a.ascale = p->action_scalar; a.inv_ascale = 1.0 / p->action_scalar;
+    a.zero_bytes = 16384;
+    a.off_tiles = 0;
+    a.off_masks = align16((size_t)2 * a.TS * 16);
+    a.off_lists = align16(a.off_masks + (size_t)256 * a.WT * 4);
+    a.off_cnt = align16(a.off_lists + (size_t)a.RT * a.CAP * 4);
+    a.off_zero = (unsigned)((a.off_cnt + (size_t)a.RT * 4 + 127) & ~(size_t)127);
+    a.off_bar = align16(a.off_zero + a.zero_bytes);
+    const size_t smem = (size_t)a.off_bar + 16;
+
+    CUDA_TRY(cudaMemsetAsync(a.counters, 0, (size_t)E * 4, st));
+    flock::flock_prep_kernel<<<dim3(L.PB, E), flock::PREP_THREADS, 0, st>>>(a, sizeof(T) == 4 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    const bool knn = a.obs != nullptr;
+    const dim3 grid((row_hi - row_lo + a.RT - 1) / a.RT, E);
+    switch (lanes) {
+        case 8: return swarm_launch<T, 8>(a, knn, grid, smem, st);
+        case 16: return swarm_launch<T, 16>(a, knn, grid, smem, st);
+        default: return swarm_launch<T, 32>(a, knn, grid, smem, st);
+    }
+}
+
 }  // namespace
 
 // ---- host-buffer context -------------------------------------------------------------------------------
@@ -270,6 +366,21 @@ int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *
                       float *values, float *network, float *reward, float *rewards_all, float *obs,
                       int32_t *final_in_b, void *stream) {
     return rollout_impl<float>(p, steps, x_a, x_b, u_a, u_b, values, network, reward, rewards_all, obs, final_in_b, stream);
+}
+
+size_t flock_swarm_scratch_bytes(const FlockParams *p) {
+    if (!p || p->n_envs < 1 || p->n_agents < 1) return 0;
+    return swarm_layout(p->n_envs, p->n_agents).bytes;
+}
+int flock_swarm_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
+                         double *network, double *reward, double *u_next, double *obs, void *scratch,
+                         size_t scratch_bytes, void *stream) {
+    return swarm_step_impl<double>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, scratch, scratch_bytes, stream);
+}
+int flock_swarm_step_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, float *values,
+                         float *network, float *reward, double *u_next, float *obs, void *scratch, size_t scratch_bytes,
+                         void *stream) {
+    return swarm_step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, scratch, scratch_bytes, stream);
 }
 
 void *flock_host_alloc(size_t bytes) {

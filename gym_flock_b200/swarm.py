@@ -35,7 +35,7 @@ def shard_rows(n_agents: int, world: int, rank: int) -> tuple:
 class SwarmEnv:
     def __init__(self, env_id: str = "Flocking-v0", n_agents: int = 65536, precision: str = "fp32",
                  device=None, group=None, comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
-                 adjacency_mode: str = "dense", row_backend=None, lanes: int = 0):
+                 adjacency_mode: str = "dense", row_backend=None, lanes: int = 32, streaming: bool | None = None):
         if env_id not in _IDS:
             raise KeyError(env_id)
         self.knn = _IDS[env_id]
@@ -58,7 +58,21 @@ class SwarmEnv:
             self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
             self._params = _lib.make_params(1, self.N, comm_radius=comm_radius, dt=dt, centralized=centralized,
                                             exact=self.exact, knn_obs=self.knn, rows=(self.lo, self.hi), lanes=lanes)
-            self._fn = _lib.lib().flock_step_f64 if self.dtype == torch.float64 else _lib.lib().flock_step_f32
+            # Swarms that one CTA can stage use the env-resident kernel; larger ones (and streaming=True) the
+            # streaming swarm kernel.  `lanes` is fixed (not derived from the shard size) so that every world size
+            # performs bit-identical row arithmetic.
+            self.streaming = (self.N > 2048) if streaming is None else bool(streaming)
+            if self.streaming and self.exact:
+                raise ValueError("fp64-exact is offered by the env-resident path only (N <= ~3000)")
+            L = _lib.lib()
+            if self.streaming:
+                self._fn = L.flock_swarm_step_f64 if self.dtype == torch.float64 else L.flock_swarm_step_f32
+                nbytes = int(L.flock_swarm_scratch_bytes(ctypes.byref(self._params)))
+                self._scratch = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+                self._scratch_ptr = (self._scratch.data_ptr() + 255) & ~255
+                self._scratch_bytes = nbytes
+            else:
+                self._fn = L.flock_step_f64 if self.dtype == torch.float64 else L.flock_step_f32
         else:
             self.device = torch.device("cpu")
         n, rows, dev, f64 = self.N, self.hi - self.lo, self.device, torch.float64
@@ -101,11 +115,19 @@ class SwarmEnv:
             self.reward.fill_(float(out["reward"]))
             return
         p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            self._lib.check(self._fn(ctypes.byref(self._params), p(x_in), p(u_in), p(x_out),
-                                     self._shifted(self.values, 6), self._shifted(self.network, self.N), p(self.reward),
-                                     p(u_next), self._shifted(self.obs, 28),
-                                     ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            if self.streaming:
+                if x_out is None:                      # reset(): the streaming path always publishes x'
+                    x_out = self._x[self._cur ^ 1]
+                self._lib.check(self._fn(ctypes.byref(self._params), p(x_in), p(u_in), p(x_out),
+                                         self._shifted(self.values, 6), self._shifted(self.network, self.N),
+                                         p(self.reward), p(u_next), self._shifted(self.obs, 28),
+                                         ctypes.c_void_p(self._scratch_ptr), ctypes.c_size_t(self._scratch_bytes), stream))
+            else:
+                self._lib.check(self._fn(ctypes.byref(self._params), p(x_in), p(u_in), p(x_out),
+                                         self._shifted(self.values, 6), self._shifted(self.network, self.N),
+                                         p(self.reward), p(u_next), self._shifted(self.obs, 28), stream))
 
     def _gather_actions(self, u_full):
         """In-place all-gather of the rows each rank just computed (equal shards, rank order = row order)."""

@@ -106,6 +106,20 @@ int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *
                       float *values, float *network, float *reward, float *rewards_all, float *obs,
                       int32_t *final_in_b, void *stream);
 
+/* Large swarms (N beyond what one CTA can stage, e.g. 65 536 agents): same semantics as flock_step_* (x_out is
+ * required), computed by an O(N) preparation kernel plus a row kernel that streams all agents' positions through
+ * shared memory with TMA bulk loads.  `scratch` is caller-owned device memory of flock_swarm_scratch_bytes(p) bytes,
+ * 256-byte aligned; its contents need not survive between calls.  FLOCK_EXACT_ORDER is not offered here;
+ * lanes must be 8, 16 or 32 (0 = 32; use the same value on every rank for shard-independent bits).
+ * Replaces the same reference lines as flock_step_* for a single giant swarm (BASELINE config 5). */
+size_t flock_swarm_scratch_bytes(const FlockParams *p);
+int flock_swarm_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
+                         double *network, double *reward, double *u_next, double *obs, void *scratch,
+                         size_t scratch_bytes, void *stream);
+int flock_swarm_step_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, float *values,
+                         float *network, float *reward, double *u_next, float *obs, void *scratch, size_t scratch_bytes,
+                         void *stream);
+
 /* ---- host-buffer context API (what a NumPy-only binding uses; no torch needed) ----------------
  * A context owns device buffers + pinned staging for (E, N); calls take HOST pointers, copy in,
  * launch, copy out and synchronise before returning.  dtype_bytes = 8 (f64) or 4 (f32).

@@ -52,3 +52,48 @@ def test_swarm_env_single_rank_matches_vec_env():
         (o2, n2), r2, _, _ = ve.step(ve.controller())
     torch.cuda.synchronize()
     assert torch.equal(sw.x, ve.x[0]) and torch.equal(o1, o2[0]) and torch.equal(n1, n2[0]) and torch.equal(r1, r2)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n,knn", [(512, True), (5000, True), (4097, False)])
+def test_streaming_swarm_kernel_vs_oracle_and_shards(precision, n, knn):
+    """The streaming swarm path (prep kernel + TMA-tiled row kernel): parity with the oracle (teacher-forced), and row
+    shards (emulated ranks, sequential launches) bit-identical to the unsharded call."""
+    import torch
+    from gym_flock_b200 import SwarmEnv
+    from gym_flock_b200.synthetic import initial_state
+    from parity_util import check_pass
+    from oracle import c_oracle
+    x0 = initial_state(n, seed=n, law="density", min_dist=0.1)
+    env_id = "Flocking-v0" if knn else "FlockingRelative-v0"
+    sw = SwarmEnv(env_id, n_agents=n, precision=precision, streaming=True)
+    sw.reset(x0)
+    u0 = sw.u.clone()
+    (obs, net), rew, _, _ = sw.step()
+    torch.cuda.synchronize()
+    x1 = c_oracle.integrate(x0, u0.cpu().numpy())
+    assert np.array_equal(sw.x.cpu().numpy(), x1)                     # the integrator is the reference's, exactly
+    check_pass(x1, sw.values.cpu().numpy(), net.cpu().numpy(), sw.u.cpu().numpy(), float(rew), precision)
+    if knn:
+        ref_obs = c_oracle.knn_obs(x1)
+        same = np.isclose(obs.cpu().numpy(), ref_obs, rtol=0, atol=1e-4 if precision == "fp32" else 1e-9).all(axis=1)
+        assert same.mean() > 0.98
+    if n % 4 == 0:      # equal shards
+        lo, hi = n // 4, n // 2
+        from gym_flock_b200 import _lib
+        part = SwarmEnv.__new__(SwarmEnv)
+        part.__dict__.update(sw.__dict__)
+        part.lo, part.hi = lo, hi
+        part._params = _lib.make_params(1, n, knn_obs=knn, rows=(lo, hi), lanes=32)
+        part.values = torch.zeros(hi - lo, 6, dtype=sw.dtype, device=sw.device)
+        part.network = torch.zeros(hi - lo, n, dtype=sw.dtype, device=sw.device)
+        part.obs = torch.zeros(hi - lo, 28, dtype=sw.dtype, device=sw.device) if knn else None
+        part._x = [torch.as_tensor(x0, device=sw.device).clone(), torch.zeros_like(sw.x)]
+        part._u = [u0.clone(), torch.zeros_like(u0)]
+        part._cur = 0
+        part.reward = torch.zeros_like(sw.reward)
+        part._launch(part._x[0], part._u[0], part._x[1], part._u[1])
+        torch.cuda.synchronize()
+        assert torch.equal(part._x[1], sw.x)
+        assert torch.equal(part.values, sw.values[lo:hi]) and torch.equal(part.network, net[lo:hi])
+        assert torch.equal(part._u[1][lo:hi], sw.u[lo:hi]) and torch.equal(part.reward, rew)
