@@ -38,6 +38,8 @@ CONFIGS = {
     "C4": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64"),
     "C4x": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64-exact"),
     "C1g": dict(env_id="Flocking-v0", E=1, N=100, precision="fp64-exact"),
+    # single giant swarm: rows sharded over the ranks, one all-gather of the actions per step (constant density)
+    "C5": dict(env_id="Flocking-v0", E=1, N=65536, precision="fp32", swarm=True),
 }
 
 
@@ -174,7 +176,76 @@ def bench_config(cfg, name, gpus):
             "l2": "each step writes more than the 126 MB L2 (inputs+outputs > L2); no explicit flush"}
 
 
+def run_swarm(args, cfg, rank, world, local_rank):
+    """C5: one swarm of N agents, rows sharded over the ranks (strong scaling: total work fixed)."""
+    import torch
+    from gym_flock_b200 import SwarmEnv
+    from gym_flock_b200.synthetic import initial_states_fast
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    N, prec = cfg["N"], cfg["precision"]
+    K, W = max(1, args.steps), max(3, args.warmup)
+    x0 = initial_states_fast(1, N, seed=1234, law="density")[0]
+    env = SwarmEnv(cfg["env_id"], n_agents=N, precision=prec, device=f"cuda:{local_rank}",
+                   adjacency_mode=args.adjacency, lanes=args.lanes)
+    env.reset(x0)
+    for _ in range(W):
+        env.step()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        env.step()                       # prep + row kernel (+ NCCL all-gather of the actions when world > 1)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=env.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        rows = N // world
+        tb = 4 if prec == "fp32" else 8
+        dense = args.adjacency == "dense"
+        alg = rows * tb * ((N if dense else 0) + 38 * N // max(N, 1) * 38) if False else rows * tb * ((N if dense else 0) + 38) + N * 8 * 6
+        step_s = ms * 1e-3 / K
+        out = {"metric": METRIC, "value": N * N * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 filter, f64 refine, f64 state", "data": "synthetic", "agent_steps_per_sec": N * K / (ms * 1e-3),
+               "config": {"workload": f"C5: {cfg['env_id']} single swarm of {N} agents (constant density), {prec}, "
+                                      f"adjacency {args.adjacency}, rows sharded x{world}, all-gather of actions per step",
+                          "n_agents": N, "rows_per_gpu": rows, "precision": prec,
+                          "parallelism": f"agent rows sharded x{world} + 1 NCCL all-gather/step",
+                          "l2": "per-GPU outputs exceed L2 when the dense adjacency is written"},
+               "roofline": {"bound": "hbm", "achieved": alg / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": alg / step_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg, "kernel": "flock_swarm_kernel (per GPU)",
+                            "avg_launch_us": step_s * 1e6},
+               "cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                "sample": "n/a: the reference materialises diff[N,N,4] = 137 GB at N=65536 (cannot run)"},
+               "e2e": None, "gpu_launches": 2 * K, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args, cfg, rank, world, local_rank):
+    if cfg.get("swarm"):
+        return run_swarm(args, cfg, rank, world, local_rank)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:       # before CUDA init (fork-safe)
         r, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=8, steps=20)
@@ -294,6 +365,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=8, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()

@@ -135,22 +135,26 @@ __device__ __forceinline__ bool refine_exact(const double4 xi, const double4 xj,
     return a;
 }
 
-// Fast refine (fp64, fused): one reciprocal instead of four divides.
+// Fast refine (fp64, fused): one reciprocal instead of four divides.  Candidates are a superset (conservative fp32
+// filter, possibly an inflated kNN radius), so pairs beyond both radii leave early.
 __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, const double R2, const double Rm,
                                             Acc &A) {
     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
     const double r2 = fma(dx, dx, dy * dy);
-    const double inv2 = Tr<double>::rcp(r2);
     const bool a = r2 < R2;
-    if (a) {
-        const double inv4 = inv2 * inv2;
-        A.f0 += xi.z - xj.z; A.f3 += xi.w - xj.w;
-        A.f1 = fma(dx, inv4, A.f1); A.f2 = fma(dx, inv2, A.f2);
-        A.f4 = fma(dy, inv4, A.f4); A.f5 = fma(dy, inv2, A.f5);
-    }
-    if (r2 <= Rm) {
-        const double c = fma(-inv2, inv2, inv2);   // 1/r2 - 1/r4
-        A.gx = fma(dx, c, A.gx); A.gy = fma(dy, c, A.gy);
+    const bool g = r2 <= Rm;
+    if (a || g) {
+        const double inv2 = Tr<double>::rcp(r2);
+        if (a) {
+            const double inv4 = inv2 * inv2;
+            A.f0 += xi.z - xj.z; A.f3 += xi.w - xj.w;
+            A.f1 = fma(dx, inv4, A.f1); A.f2 = fma(dx, inv2, A.f2);
+            A.f4 = fma(dy, inv4, A.f4); A.f5 = fma(dy, inv2, A.f5);
+        }
+        if (g) {
+            const double c = fma(-inv2, inv2, inv2);   // 1/r2 - 1/r4
+            A.gx = fma(dx, c, A.gx); A.gy = fma(dy, c, A.gy);
+        }
     }
     return a;
 }

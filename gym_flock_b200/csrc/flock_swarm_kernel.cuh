@@ -193,13 +193,15 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     const double *tot = a.totals + (size_t)env * 8;
     const float pxi = (float)(xi.x - tot[5]), pyi = (float)(xi.y - tot[6]);     // same rounding as the packed array
     const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
-    const float tc = (float)a.thrC, rc = sqrtf(tc);
+    // Flocking-v0: the 7 nearest neighbours are searched among the candidates, so the candidate radius is inflated
+    // (x4 in r2: ~36 candidates per row at the reference density); rows that still find fewer than 7 rescan all agents.
+    const float tc = (float)a.thrC * (KNN ? 4.0f : 1.0f), rc = sqrtf(tc);
     const float thrA = tc * (1.0f + 2e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
     unsigned *mrow = masks + (size_t)tid * a.WT;
     unsigned *lrow = lists + (size_t)rl * a.CAP;
     Acc A;
     A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
-    TopK<float> top;
+    TopK<double> top;                                       // kNN by exact fp64 r2 over the candidates
     if constexpr (KNN) top.init(i);
     const bool cen = a.centralized != 0;
 
@@ -222,7 +224,6 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                 const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
                 bits |= (r2.x <= thrA) ? (1u << (2 * q)) : 0u;
                 bits |= (r2.y <= thrA) ? (2u << (2 * q)) : 0u;
-                if constexpr (KNN) { top.insert(r2.x, 2 * (s0 + m)); top.insert(r2.y, 2 * (s0 + m) + 1); }
             };
             if (qe == 16) {
 #pragma unroll
@@ -245,6 +246,10 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                 const int j = 2 * (s0 + sub + LANES * (kk >> 1)) + (kk & 1);
                 if (j == i || j >= N) continue;
                 const double4 xj = ld_state(xc + (size_t)j * 4);
+                if constexpr (KNN) {
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    top.insert(fma(dx, dx, dy * dy), j);
+                }
                 if (refine_fast(xi, xj, a.R2, a.Rm, A)) {
                     const int pos = atomicAdd(&lcnt[rl], 1);
                     if (pos < a.CAP) lrow[pos] = (unsigned)j;
@@ -287,30 +292,46 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     // ---- kNN observation ------------------------------------------------------------------------------------------------
     if constexpr (KNN) {
         int nb[TOPK];
+        auto merge = [&](int *out) {                         // every lane of the row ends with the row's sorted ids
 #pragma unroll
-        for (int m = 0; m < TOPK; ++m) {
-            float bd = top.d[0]; int bi = top.id[0];
+            for (int m = 0; m < TOPK; ++m) {
+                double bd = top.d[0]; int bi = top.id[0];
 #pragma unroll
-            for (int s = LANES / 2; s > 0; s >>= 1) {
-                const float od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
-                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                for (int s = LANES / 2; s > 0; s >>= 1) {
+                    const double od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                }
+                if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
+                out[m] = bi;
             }
-            if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
-            nb[m] = bi;
+        };
+        merge(nb);
+        // fewer than 7 neighbours inside the inflated radius (flock edge, sparse swarm): rescan ALL agents for this row
+        const bool need = valid && (nb[KNN_K - 1] == i);
+        if (__any_sync(0xffffffffu, need)) {
+            top.init(i);
+            if (need) {
+                for (int j = sub; j < N; j += LANES) {
+                    if (j == i) continue;
+                    const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
+                    const double dx = xi.x - pj.x, dy = xi.y - pj.y;
+                    top.insert(fma(dx, dx, dy * dy), j);
+                }
+            }
+            int nb2[TOPK];
+            merge(nb2);
+            if (need) {
+#pragma unroll
+                for (int m = 0; m < TOPK; ++m) nb[m] = nb2[m];
+            }
         }
         if (valid && sub == 0 && a.obs) {
             TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
-            int m = 0;
-            bool dropped = false;
 #pragma unroll
-            for (int q = 0; q < TOPK; ++q) {
-                if (!dropped && nb[q] == i) { dropped = true; continue; }
-                if (m < KNN_K) {
-                    const double4 xn = ld_state(xc + (size_t)min(nb[q], N - 1) * 4);
-                    o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                    o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
-                    ++m;
-                }
+            for (int m = 0; m < KNN_K; ++m) {                 // the diagonal is never a candidate here; unused slots hold i
+                const double4 xn = ld_state(xc + (size_t)min(nb[m], N - 1) * 4);
+                o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
             }
         }
     }
