@@ -194,6 +194,7 @@ def run_swarm(args, cfg, rank, world, local_rank):
     env.reset(x0)
     for _ in range(W):
         env.step()
+    env._skip_gather = bool(args.skip_gather)
 
     def barrier():
         if dist is not None:
@@ -365,7 +366,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=8, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
+    ap.add_argument("--skip-gather", type=int, default=0, help="C5 diagnostic: skip the all-gather (results wrong; timing only)")
+    ap.add_argument("--lanes", type=int, default=16, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()

@@ -204,7 +204,7 @@ int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, doub
 
 
 // ---- large swarms: prep kernel + streaming row kernel (flock_swarm_kernel.cuh) --------------------------------------
-struct SwarmLayout { size_t off_pf, off_partials, off_totals, off_counters, bytes; int NP2, PB; };
+struct SwarmLayout { size_t off_pf, off_partials, off_totals, off_counters, off_needy, bytes; int NP2, PB; };
 
 SwarmLayout swarm_layout(int E, int N) {
     SwarmLayout L;
@@ -214,7 +214,9 @@ SwarmLayout swarm_layout(int E, int N) {
     L.off_partials = ((size_t)E * L.NP2 * 16 + 255) & ~(size_t)255;
     L.off_totals = L.off_partials + (((size_t)E * L.PB * 32 + 255) & ~(size_t)255);
     L.off_counters = L.off_totals + (((size_t)E * 64 + 255) & ~(size_t)255);
-    L.bytes = L.off_counters + (((size_t)E * 4 + 255) & ~(size_t)255);
+    // counters: [E] reduction tickets, then [E] needy-row counts (cleared together every step)
+    L.off_needy = L.off_counters + (((size_t)E * 8 + 255) & ~(size_t)255);
+    L.bytes = L.off_needy + (size_t)E * flock::NEEDY_CAP * 4;
     return L;
 }
 
@@ -267,6 +269,8 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.partials = reinterpret_cast<double *>(sc + L.off_partials);
     a.totals = reinterpret_cast<double *>(sc + L.off_totals);
     a.counters = reinterpret_cast<unsigned *>(sc + L.off_counters);
+    a.needy_cnt = a.counters + E;
+    a.needy_rows = reinterpret_cast<unsigned *>(sc + L.off_needy);
     a.E = E; a.N = N; a.NP2 = L.NP2; a.PB = L.PB; a.row_lo = row_lo; a.row_hi = row_hi;
     a.RT = 256 / lanes;
     a.TS = 2048;
@@ -285,16 +289,22 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.off_bar = align16(a.off_zero + a.zero_bytes);
     const size_t smem = (size_t)a.off_bar + 16;
 
-    CUDA_TRY(cudaMemsetAsync(a.counters, 0, (size_t)E * 4, st));
+    CUDA_TRY(cudaMemsetAsync(a.counters, 0, (size_t)E * 8, st));
     flock::flock_prep_kernel<<<dim3(L.PB, E), flock::PREP_THREADS, 0, st>>>(a, sizeof(T) == 4 ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     const bool knn = a.obs != nullptr;
     const dim3 grid((row_hi - row_lo + a.RT - 1) / a.RT, E);
+    int rc;
     switch (lanes) {
-        case 8: return swarm_launch<T, 8>(a, knn, grid, smem, st);
-        case 16: return swarm_launch<T, 16>(a, knn, grid, smem, st);
-        default: return swarm_launch<T, 32>(a, knn, grid, smem, st);
+        case 8: rc = swarm_launch<T, 8>(a, knn, grid, smem, st); break;
+        case 16: rc = swarm_launch<T, 16>(a, knn, grid, smem, st); break;
+        default: rc = swarm_launch<T, 32>(a, knn, grid, smem, st); break;
     }
+    if (rc || !knn) return rc;
+    // rows whose kNN search found fewer than 7 agents inside the inflated radius: one CTA per row rescans everything
+    flock::flock_knn_fix_kernel<T><<<dim3(128, E), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
 }
 
 }  // namespace

@@ -33,6 +33,8 @@ struct SArgs {
     double *partials;       // scratch: [E][PB][4]
     double *totals;         // scratch: [E][8]  (ref vx, ref vy, sum vx, sum vy, reward, ref px, ref py, pad)
     unsigned *counters;     // scratch: [E] tickets of the two-stage reduction (zero between launches)
+    unsigned *needy_cnt;    // scratch: [E] rows whose kNN search needs a full rescan (cleared every step)
+    unsigned *needy_rows;   // scratch: [E][NEEDY_CAP]
     int E, N, NP2, PB;
     int row_lo, row_hi;
     int RT;                 // rows per CTA (256 / LANES)
@@ -46,6 +48,7 @@ struct SArgs {
 };
 
 constexpr int PREP_THREADS = 256;
+constexpr int NEEDY_CAP = 8192;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
 
 // ---- mbarrier / TMA load helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -306,8 +309,19 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
             }
         };
         merge(nb);
-        // fewer than 7 neighbours inside the inflated radius (flock edge, sparse swarm): rescan ALL agents for this row
-        const bool need = valid && (nb[KNN_K - 1] == i);
+        // Fewer than 7 neighbours inside the inflated radius (flock edge, stray agents): the row is queued for
+        // flock_knn_fix_kernel, which rescans ALL agents with a whole CTA per row after this kernel (so the few such
+        // rows do not stretch this kernel's tail).  If the queue is full the row rescans here.
+        bool need = valid && (nb[KNN_K - 1] == i);
+        if (need && a.obs) {
+            unsigned slot = 0;
+            if (sub == 0) slot = atomicAdd(a.needy_cnt + env, 1u);
+            slot = __shfl_sync(__activemask(), slot, (lane / LANES) * LANES);
+            if (slot < (unsigned)NEEDY_CAP) {
+                if (sub == 0) a.needy_rows[(size_t)env * NEEDY_CAP + slot] = (unsigned)i;
+                need = false;
+            }
+        }
         if (__any_sync(0xffffffffu, need)) {
             top.init(i);
             if (need) {
@@ -352,6 +366,54 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                 if (fma(dx, dx, dy * dy) < a.R2) orow[j] = idg;
             }
         }
+    }
+}
+
+// ---- kNN fix-up: one CTA per queued row rescans all agents (exact fp64 r2, ties to the lower index) -----------------
+template <typename TO>
+__global__ void __launch_bounds__(256) flock_knn_fix_kernel(const SArgs a) {
+    const int env = blockIdx.y;
+    const unsigned cnt = min(a.needy_cnt[env], (unsigned)NEEDY_CAP);
+    __shared__ double sd[8 * TOPK];
+    __shared__ int si[8 * TOPK];
+    const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *xc = a.x_cur + (size_t)env * N * 4;
+    for (unsigned q = blockIdx.x; q < cnt; q += gridDim.x) {
+        const int i = (int)a.needy_rows[(size_t)env * NEEDY_CAP + q];
+        const double4 xi = ld_state(xc + (size_t)i * 4);
+        TopK<double> top;
+        top.init(i);
+        for (int j = tid; j < N; j += 256) {
+            if (j == i) continue;
+            const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
+            const double dx = xi.x - pj.x, dy = xi.y - pj.y;
+            top.insert(fma(dx, dx, dy * dy), j);
+        }
+#pragma unroll
+        for (int m = 0; m < TOPK; ++m) {                     // warp merge: the warp's TOPK best, in order
+            double bd = top.d[0]; int bi = top.id[0];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const double od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
+            if (lane == 0) { sd[warp * TOPK + m] = bd; si[warp * TOPK + m] = bi; }
+        }
+        __syncthreads();
+        if (tid == 0 && a.obs) {                             // 64 entries: one thread finishes the merge
+            TopK<double> fin;
+            fin.init(i);
+            for (int e = 0; e < 8 * TOPK; ++e) if (si[e] != i) fin.insert(sd[e], si[e]);
+            // equal r2: insert keeps the earlier entry in front; entries arrive in warp order, not index order
+            TO *o = reinterpret_cast<TO *>(a.obs) + ((size_t)env * N + i) * (NXS * KNN_K);
+            for (int m = 0; m < KNN_K; ++m) {
+                const double4 xn = ld_state(xc + (size_t)fin.id[m] * 4);
+                o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+            }
+        }
+        __syncthreads();
     }
 }
 

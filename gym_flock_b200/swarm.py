@@ -15,6 +15,7 @@ gloo without a GPU; the product path (row_backend=None) is the CUDA kernel and r
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -45,10 +46,15 @@ class SwarmEnv:
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
         self.lo, self.hi = shard_rows(self.N, self.world, self.rank)
+        emu = os.environ.get("FLOCK_EMULATE_SHARD")          # diagnostics: "rank,world" -> time one shard on one GPU
+        if emu and not self.distributed:
+            r, w = (int(v) for v in emu.split(","))
+            self.lo, self.hi = shard_rows(self.N, w, r)
         self.dtype, self.exact = _PREC[precision]
         self.precision = precision
         self.centralized, self.comm_radius, self.dt = bool(centralized), float(comm_radius), float(dt)
         self.row_backend = row_backend
+        self._skip_gather = False        # diagnostics only
         self.adjacency_mode = adjacency_mode
         if row_backend is None:
             if not torch.cuda.is_available():
@@ -57,7 +63,8 @@ class SwarmEnv:
             self._lib = _lib
             self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
             self._params = _lib.make_params(1, self.N, comm_radius=comm_radius, dt=dt, centralized=centralized,
-                                            exact=self.exact, knn_obs=self.knn, rows=(self.lo, self.hi), lanes=lanes)
+                                            exact=self.exact, knn_obs=self.knn, rows=(self.lo, self.hi),
+                                            lanes=1 if self.exact else lanes)
             # Swarms that one CTA can stage use the env-resident kernel; larger ones (and streaming=True) the
             # streaming swarm kernel.  `lanes` is fixed (not derived from the shard size) so that every world size
             # performs bit-identical row arithmetic.
@@ -131,7 +138,7 @@ class SwarmEnv:
 
     def _gather_actions(self, u_full):
         """In-place all-gather of the rows each rank just computed (equal shards, rank order = row order)."""
-        if self.world > 1:
+        if self.world > 1 and not self._skip_gather:
             dist.all_gather_into_tensor(u_full, u_full[self.lo:self.hi].clone(), group=self.group)
 
     def _observation(self):

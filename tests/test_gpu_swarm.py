@@ -97,3 +97,26 @@ def test_streaming_swarm_kernel_vs_oracle_and_shards(precision, n, knn):
         assert torch.equal(part._x[1], sw.x)
         assert torch.equal(part.values, sw.values[lo:hi]) and torch.equal(part.network, net[lo:hi])
         assert torch.equal(part._u[1][lo:hi], sw.u[lo:hi]) and torch.equal(part.reward, rew)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_streaming_swarm_sparse_rows_use_knn_fixup(precision):
+    """A sparse swarm: most rows have fewer than 7 agents inside the inflated candidate radius, so their kNN
+    observation comes from the fix-up kernel (full rescan).  Must equal the oracle's argsort-based observation."""
+    import torch
+    from gym_flock_b200 import SwarmEnv
+    from oracle import c_oracle
+    rs = np.random.RandomState(11)
+    n = 3000
+    x0 = np.zeros((n, 4))
+    x0[:, :2] = rs.uniform(-60, 60, size=(n, 2))          # ~0.2 agents per unit area
+    x0[:, 2:] = rs.uniform(-1, 1, size=(n, 2))
+    sw = SwarmEnv("Flocking-v0", n_agents=n, precision=precision, streaming=True)
+    obs, net = sw.reset(x0)
+    torch.cuda.synchronize()
+    ref = c_oracle.knn_obs(x0)
+    tol = 1e-4 if precision == "fp32" else 1e-10
+    err = np.abs(obs.cpu().numpy() - ref).max(axis=1) / np.abs(ref).max()
+    assert (err <= tol).all(), (int((err > tol).sum()), float(err.max()))
+    h = c_oracle.helpers(x0)
+    assert np.array_equal(net.cpu().numpy() > 0, h["adj_mean"] > 0)
