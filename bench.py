@@ -38,6 +38,7 @@ CONFIGS = {
     "C4": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64"),
     "C4x": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64-exact"),
     "C1g": dict(env_id="Flocking-v0", E=1, N=100, precision="fp64-exact"),
+    "C2k": dict(env_id="Flocking-v0", E=4096, N=100, precision="fp32"),            # C2 with the kNN observation
     # single giant swarm: rows sharded over the ranks, one all-gather of the actions per step (constant density)
     "C5": dict(env_id="Flocking-v0", E=1, N=65536, precision="fp32", swarm=True),
 }
