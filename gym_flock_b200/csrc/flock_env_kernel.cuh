@@ -29,6 +29,9 @@
 // batches still fill 148 SMs.
 #pragma once
 #include <type_traits>
+#ifndef FLOCK_MAXT
+#define FLOCK_MAXT 256
+#endif
 #ifndef FLOCK_MINB
 #define FLOCK_MINB 4   // resident 256-thread CTAs per SM the fast kernels are compiled for (register cap)
 #endif
@@ -238,7 +241,7 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, co
 // Resident-CTA targets: the fast kernels are latency bound (divergent refine loops), so occupancy matters more than
 // registers: 256-thread bound, 6 CTAs (48 warps) per SM -> <= 40 registers.  EXACT keeps its registers.
 template <typename TO, int LANES, bool EXACT, bool KNN>
-__global__ void __launch_bounds__(256, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
+__global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
     constexpr bool PA32 = std::is_same<TO, float>::value;   // phase A on packed fp32 positions
     using TK = typename std::conditional<PA32, float, double>::type;
     static_assert(!EXACT || (!PA32 && LANES == 1), "EXACT is fp64, one thread per row");

@@ -333,6 +333,34 @@ class FlockingEnv(FlockingRelativeEnv):
         return self.get_observation(), self.state_network
 
 
+def _grid(n, side=5):
+    """Initial lattice of the two-flocks variant (gym_flock/envs/flocking/utils.py:23-31): 0.8 x (col - side/2, row - rows/2)."""
+    rows = int(n / side)
+    xs, ys = np.meshgrid(np.arange(0, side) - side / 2.0, np.arange(0, rows) - rows / 2.0)
+    return 0.8 * np.hstack((xs.reshape((n, 1)), ys.reshape((n, 1))))
+
+
+class FlockingTwoFlocksEnv(FlockingRelativeEnv):
+    """gym-flock's 'FlockingTwoFlocks-v0' (flocking_twoflocks.py:8-26): same dynamics and kernel, lattice reset with
+    velocities pointing at the origin plus a common random bias (one draw of size 2 from the global np.random)."""
+
+    def reset(self):
+        n = self.n_agents
+        x = np.zeros((n, self.nx_system))
+        bias = np.random.uniform(low=-self.v_bias / 2.0, high=self.v_bias / 2.0, size=(2,))
+        grids = _grid(n, side=int(n / 10))
+        x[:, 0:2] = grids
+        x[:, 2:4] = -grids
+        x[:, 2] = x[:, 2] + bias[0]
+        x[:, 3] = x[:, 3] + bias[1]
+        self.mean_vel = np.mean(x[:, 2:4], axis=0)
+        self._x = x
+        self._shadow = None
+        self.init_vel = self._x[:, 2:4]
+        self.compute_helpers()
+        return (self.state_values, self.state_network)
+
+
 class TimeLimit:
     """What gym.make() wraps the env in (gym 0.11-era API): counts steps, forces done=True once
     max_episode_steps is reached, forwards everything else; the raw env is `.env`."""
@@ -363,9 +391,10 @@ class TimeLimit:
         return getattr(self.env, name)
 
 
-REGISTRY = {   # gym_flock/__init__.py:53-63
+REGISTRY = {   # gym_flock/__init__.py:53-63, 90-94
     'Flocking-v0': (FlockingEnv, 1000),
     'FlockingRelative-v0': (FlockingRelativeEnv, 1000),
+    'FlockingTwoFlocks-v0': (FlockingTwoFlocksEnv, 500),   # SURVEY.md 8f "next #1": same kernel, different reset
 }
 
 

@@ -89,7 +89,7 @@ def test_drop_in_surface_and_synthetic_states():
                           nx_system=4, n_features=6, nu=2, mean_pooling=True, centralized=True).items():
         assert getattr(env, attr) == val
     assert abs(env.comm_radius2 - 0.81) < 1e-15 and isinstance(env.seed(5), list)
-    assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0"}
+    assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0", "FlockingTwoFlocks-v0"}
     with pytest.raises(KeyError):
         gf.make("Shepherding-v0")
     a, b = initial_state(50, seed=7, min_dist=0.1), initial_states(2, 50, seed=7, min_dist=0.1)

@@ -133,3 +133,19 @@ def test_vec_env_matches_host_engine_and_rollout():
             assert torch.equal(vec2.x, vec.x) and torch.equal(vec2.values, vec.values)
             assert torch.equal(rewards[-1], vec.reward)
             host.close()
+
+
+def test_two_flocks_variant_runs_and_matches_oracle():
+    import gym_flock_b200 as gf
+    from oracle import c_oracle
+    env = gf.make('FlockingTwoFlocks-v0')
+    assert env._max_episode_steps == 500
+    np.random.seed(4)
+    values, net = env.reset()
+    x0 = env.env.x.copy()
+    assert np.array_equal(values, c_oracle.helpers(x0)["values"])
+    for _ in range(5):
+        (values, net), r, done, _ = env.step(env.env.controller())
+    ref = c_oracle.rollout(x0, 5)
+    assert np.array_equal(env.env.x, ref["x"]) and np.array_equal(values, ref["values"]) and np.array_equal(net, ref["adj_mean"])
+    env.close()

@@ -41,3 +41,25 @@ def test_reference_reset_cfg_path_matches_golden_x0():
     env.reset()
     g = np.load(os.path.join(GOLDEN_DIR, "smoke_seed0.npz"))
     assert np.allclose(env.x, g["x0"], rtol=0, atol=1e-12)
+
+
+def test_two_flocks_reset_law_matches_reference():
+    """FlockingTwoFlocks-v0 differs from FlockingRelative-v0 only in reset(): same lattice, same RNG draw."""
+    import importlib.util, os, sys
+    root = ref_loader.reference_root()
+    ref_loader.load()
+    for name in ("utils", "flocking_twoflocks"):
+        spec = importlib.util.spec_from_file_location(f"gym_flock.envs.flocking.{name}",
+                                                      os.path.join(root, "gym_flock/envs/flocking", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"gym_flock.envs.flocking.{name}"] = mod
+        spec.loader.exec_module(mod)
+    ref = sys.modules["gym_flock.envs.flocking.flocking_twoflocks"].FlockingTwoFlocksEnv()
+    np.random.seed(4)
+    ref.reset()
+    from gym_flock_b200.envs import _grid
+    np.random.seed(4)
+    bias = np.random.uniform(low=-ref.v_bias / 2.0, high=ref.v_bias / 2.0, size=(2,))
+    g = _grid(100, side=10)
+    x = np.zeros((100, 4)); x[:, :2] = g; x[:, 2:] = -g; x[:, 2] += bias[0]; x[:, 3] += bias[1]
+    assert np.array_equal(ref.x, x)
