@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 FLOCK_CENTRALIZED = 0x1
 FLOCK_EXACT_ORDER = 0x2
 FLOCK_KNN_OBS = 0x4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class FlockParams(ctypes.Structure):
@@ -34,7 +34,9 @@ class FlockParams(ctypes.Structure):
                 ("dt", ctypes.c_double), ("action_scalar", ctypes.c_double),
                 ("flags", ctypes.c_int32), ("knn", ctypes.c_int32),
                 ("row_lo", ctypes.c_int32), ("row_hi", ctypes.c_int32),
-                ("lanes", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("lanes", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("step_scale", ctypes.c_double), ("state_scale", ctypes.c_double), ("u_clip", ctypes.c_double),
+                ("n_leaders", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 class FlockError(RuntimeError):
@@ -126,14 +128,16 @@ def check(rc: int) -> None:
 def make_params(n_envs: int, n_agents: int, comm_radius: float = 0.9, dt: float = 0.01,
                 action_scalar: float = 10.0, centralized: bool = True, exact: bool = False,
                 knn_obs: bool = False, knn: int = 7, rows: tuple | None = None, lanes: int = 0,
-                comm_radius2: float | None = None) -> FlockParams:
+                comm_radius2: float | None = None, step_scale: float = 0.0, state_scale: float = 0.0,
+                u_clip: float = 0.0, n_leaders: int = 0) -> FlockParams:
     flags = (FLOCK_CENTRALIZED if centralized else 0) | (FLOCK_EXACT_ORDER if exact else 0) | \
             (FLOCK_KNN_OBS if knn_obs else 0)
     r2 = comm_radius * comm_radius if comm_radius2 is None else comm_radius2   # flocking_relative.py:44
     lo, hi = rows if rows is not None else (0, 0)
     return FlockParams(int(n_envs), int(n_agents), float(comm_radius), float(r2), float(dt),
                        float(action_scalar), flags, int(knn), int(lo), int(hi), int(lanes),
-                       int(os.environ.get("FLOCK_TUNE", "0")))
+                       int(os.environ.get("FLOCK_TUNE", "0")), float(step_scale), float(state_scale), float(u_clip),
+                       int(n_leaders), 0)
 
 
 def require_device() -> int:

@@ -18,6 +18,15 @@ namespace {
 
 thread_local std::string g_err;
 
+flock::StepVariant step_variant(const FlockParams *p) {
+    flock::StepVariant v;
+    v.step_scale = (p->step_scale != 0.0) ? p->step_scale : p->action_scalar;
+    v.state_scale = (p->state_scale != 0.0) ? p->state_scale : 1.0;
+    v.u_clip = p->u_clip;
+    v.n_leaders = p->n_leaders;
+    return v;
+}
+
 int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -52,6 +61,8 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     if (!p) return fail(FLOCK_EINVAL, "params is NULL");
     const int E = p->n_envs, N = p->n_agents;
     if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
+    if (p->n_leaders < 0 || p->n_leaders > N || p->u_clip < 0.0 || p->state_scale < 0.0)
+        return fail(FLOCK_EINVAL, "bad variant parameters (n_leaders=%d u_clip=%g state_scale=%g)", p->n_leaders, p->u_clip, p->state_scale);
     if ((long long)E * N > (1LL << 30)) return fail(FLOCK_EUNSUPPORTED, "E*N too large");
     int row_lo = p->row_lo, row_hi = p->row_hi;
     if (row_lo == 0 && row_hi == 0) row_hi = N;
@@ -115,7 +126,7 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     k.tune = p->reserved >> 8;
     // small full rows: expand in the warp (coalesced stores); large rows: bulk zero-fill + scatter
     k.out_mode = (lanes == 1 && nrows == N && (size_t)N * tbytes <= 2048 && !((p->reserved >> 8) & 16)) ? 1 : 0;
-    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar;
+    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
     pl.lanes = lanes; pl.threads = threads;
     pl.grid = grid;
     return FLOCK_OK;
@@ -279,7 +290,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
     a.R = p->comm_radius; a.R2 = p->comm_radius2; a.thrC = std::max(a.R, a.R2);
     a.Rm = (a.centralized || a.R2 > a.R) ? a.R : std::nextafter(a.R2, -1.0);
-    a.dt = p->dt; a.ascale = p->action_scalar; a.inv_ascale = 1.0 / p->action_scalar;
+    a.dt = p->dt; a.ascale = p->action_scalar; a.inv_ascale = 1.0 / p->action_scalar; a.var = step_variant(p);
     a.zero_bytes = 16384;
     a.off_tiles = 0;
     a.off_masks = align16((size_t)2 * a.TS * 16);

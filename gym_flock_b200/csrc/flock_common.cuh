@@ -73,6 +73,27 @@ __device__ __forceinline__ double4 integrate_exact(double4 x, double2 u, double 
     return y;
 }
 
+// The step of every flocking variant, in the reference's operation order:
+//   FlockingRelative/Flocking : a = u*10                                    flocking_relative.py:96-105
+//   FlockingLeader            : a = u, leaders (j < n_leaders) get a*0       flocking_leader.py:21-31
+//   FlockingStochastic        : u = clip(u, +-c); a = u*6; x = x*6; step; x = x/6      flocking_stoch.py:14-33
+struct StepVariant { double step_scale, state_scale, u_clip; int n_leaders; };
+__device__ __forceinline__ double4 integrate_variant(double4 x, double2 u, const int j, const double dt, const StepVariant v) {
+    if (v.u_clip > 0.0) { u.x = fmin(fmax(u.x, -v.u_clip), v.u_clip); u.y = fmin(fmax(u.y, -v.u_clip), v.u_clip); }
+    if (j < v.n_leaders) { u.x = 0.0; u.y = 0.0; }          // (u*dt*dt*0.5)*0 = 0: the position/velocity keep their drift only
+    const bool scaled = (v.state_scale != 1.0);
+    if (scaled) {
+        x.x = __dmul_rn(x.x, v.state_scale); x.y = __dmul_rn(x.y, v.state_scale);
+        x.z = __dmul_rn(x.z, v.state_scale); x.w = __dmul_rn(x.w, v.state_scale);
+    }
+    double4 y = integrate_exact(x, u, dt, v.step_scale);
+    if (scaled) {
+        y.x = __ddiv_rn(y.x, v.state_scale); y.y = __ddiv_rn(y.y, v.state_scale);
+        y.z = __ddiv_rn(y.z, v.state_scale); y.w = __ddiv_rn(y.w, v.state_scale);
+    }
+    return y;
+}
+
 __device__ __forceinline__ double4 ld_state(const double *p) {   // p 32-byte aligned (row of x)
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
     const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);

@@ -58,6 +58,7 @@ struct KArgs {
     int NP2;      // pair slots per env in the packed fp32 position array: (N + 1) / 2
     double R, R2, dt, ascale;
     double inv_ascale;   // 1/ascale (fast modes multiply; EXACT divides)
+    StepVariant var;     // flocking variants (leader / stochastic); defaults reproduce FlockingRelative
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
     unsigned off_xs, off_pf, off_masks, off_stats, off_zero;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
             double4 x = ld_state(a.x_in + ga * 4);
             if (a.u_in) {
                 const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + ga);
-                x = integrate_exact(x, u, a.dt, a.ascale);
+                const int gq = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;
+                x = integrate_variant(x, u, idx - gq * N, a.dt, a.var);
             }
             const int ge = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;     // exact: idx < 2^20
             const int j = idx - ge * N;
@@ -599,6 +601,9 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
                 const double ia = a.inv_ascale;                  // one extra rounding vs a true divide
                 ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * ia;
                 uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * ia;
+            }
+            if (a.var.u_clip > 0.0) {                    // FlockingStochastic.controller (flocking_stoch.py:43)
+                ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
             }
             reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
         }

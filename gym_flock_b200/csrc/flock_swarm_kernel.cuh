@@ -43,6 +43,7 @@ struct SArgs {
     int CAP;                // neighbour-list capacity per row
     int centralized;
     double R, R2, Rm, thrC, dt, ascale, inv_ascale;
+    StepVariant var;
     unsigned off_tiles, off_masks, off_lists, off_cnt, off_zero, off_bar;
     unsigned zero_bytes;
 };
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a,
     double sx = 0, sy = 0, qx = 0, qy = 0;
     if (j < N) {
         double4 x = ld_state(a.x_in + (e0 + j) * 4);
-        if (a.u_in) x = integrate_exact(x, __ldg(reinterpret_cast<const double2 *>(a.u_in) + e0 + j), a.dt, a.ascale);
+        if (a.u_in) x = integrate_variant(x, __ldg(reinterpret_cast<const double2 *>(a.u_in) + e0 + j), j, a.dt, a.var);
         st_state(a.x_cur + (e0 + j) * 4, x);
         float *p = reinterpret_cast<float *>(a.pf + (size_t)env * a.NP2 + (j >> 1));
         p[j & 1] = (float)(x.x - ref.x); p[2 + (j & 1)] = (float)(x.y - ref.y);
@@ -286,8 +287,11 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                 sdx = fma((double)N, xi.z - tot[0], -tot[2]);
                 sdy = fma((double)N, xi.w - tot[1], -tot[3]);
             }
-            const double ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * a.inv_ascale;
-            const double uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * a.inv_ascale;
+            double ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * a.inv_ascale;
+            double uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * a.inv_ascale;
+            if (a.var.u_clip > 0.0) {
+                ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
+            }
             reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
         }
     }

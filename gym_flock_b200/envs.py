@@ -121,6 +121,10 @@ class FlockingRelativeEnv:
     def _knn(self) -> bool:
         return False
 
+    def _variant(self) -> dict:
+        """Step-variant parameters of the C ABI (FlockParams.step_scale / state_scale / u_clip / n_leaders)."""
+        return {}
+
     def _engine(self) -> HostFlockBatch:
         key = (self.n_agents, self.comm_radius, self.comm_radius2, self.dt, self.action_scalar, self.centralized)
         if self._eng is None or self._eng_key[0] != self.n_agents:
@@ -129,7 +133,7 @@ class FlockingRelativeEnv:
             self._eng = HostFlockBatch(1, self.n_agents, comm_radius=self.comm_radius, dt=self.dt,
                                        centralized=bool(self.centralized), knn_obs=self._knn(),
                                        precision=self._precision, device=self._device,
-                                       comm_radius2=self.comm_radius2, pinned=False)
+                                       comm_radius2=self.comm_radius2, pinned=False, **self._variant())
             self._shadow = None
         elif key != self._eng_key:
             self._eng.set_params(comm_radius=self.comm_radius, comm_radius2=self.comm_radius2, dt=self.dt,
@@ -361,6 +365,78 @@ class FlockingTwoFlocksEnv(FlockingRelativeEnv):
         return (self.state_values, self.state_network)
 
 
+class FlockingLeaderEnv(FlockingRelativeEnv):
+    """gym-flock's 'FlockingLeader-v0' (flocking_leader.py:5-57): the first n_leaders agents are not actuated and the
+    action is applied unscaled (self.u = u, :24); same kernel with FlockParams.n_leaders / step_scale = 1."""
+
+    def __init__(self, precision: str = "fp64-exact", device: int = 0):
+        super().__init__(precision=precision, device=device)
+        self.n_leaders = 2                                           # :11
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:self.n_leaders] = 0
+        self.quiver = None
+        self.half_leaders = int(self.n_leaders / 2.0)
+
+    def params_from_cfg(self, args):
+        super().params_from_cfg(args)
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:self.n_leaders] = 0
+
+    def _variant(self) -> dict:
+        return dict(step_scale=1.0, n_leaders=int(self.n_leaders))
+
+    def step(self, u):
+        """flocking_leader.py:21-34."""
+        assert u.shape == (self.n_agents, self.nu)
+        self._sync_device()
+        eng = self._engine()
+        self.u = u
+        eng.step(np.asarray(u, dtype=np.float64)[None])
+        self._x = eng.x[0].copy()
+        self._shadow = self._x.copy()
+        self._pull(eng)
+        return (self.state_values, self.state_network), self.instant_cost(), False, {}
+
+    def reset(self):
+        """flocking_leader.py:36-40: the leaders get one common random velocity AFTER the helpers were computed
+        (the reference returns the features of the state before that overwrite; so do we)."""
+        out = super().reset()
+        self._x[0:self.n_leaders, 2:4] = np.ones((self.n_leaders, 2)) * np.random.uniform(
+            low=-self.v_max, high=self.v_max, size=(1, 1))
+        return out
+
+
+class FlockingStochasticEnv(FlockingRelativeEnv):
+    """gym-flock's 'FlockingStochastic-v0' (flocking_stoch.py:5-45): actions clipped to +-0.5 and scaled by 6, the state is
+    scaled by 6 around the Euler step, dt ~ N(0.12, 0.018) drawn per step from the global np.random stream."""
+
+    def __init__(self, precision: str = "fp64-exact", device: int = 0):
+        super().__init__(precision=precision, device=device)
+        self.dt_mean = 0.12
+        self.dt_sigma = 0.018
+        self.max_accel = 0.5
+        self.scale = 6.0
+
+    def _variant(self) -> dict:
+        return dict(step_scale=float(self.scale), state_scale=float(self.scale), u_clip=float(self.max_accel))
+
+    def step(self, u):
+        """flocking_stoch.py:14-35."""
+        assert u.shape == (self.n_agents, self.nu)
+        self._sync_device()
+        uc = np.clip(u, a_min=-self.max_accel, a_max=self.max_accel)
+        self.u = uc * self.scale
+        self.dt = np.random.normal(self.dt_mean, self.dt_sigma)      # one draw per step, as in the reference (:20)
+        eng = self._engine()                                          # picks up the new dt
+        eng.step(np.asarray(u, dtype=np.float64)[None])               # the kernel clips and scales (bit-identical)
+        self._x = eng.x[0].copy()
+        self._shadow = self._x.copy()
+        self._pull(eng)
+        return (self.state_values, self.state_network), self.instant_cost(), False, {}
+
+    # controller(): the kernel clips its output to +-u_clip (flocking_stoch.py:37-45)
+
+
 class TimeLimit:
     """What gym.make() wraps the env in (gym 0.11-era API): counts steps, forces done=True once
     max_episode_steps is reached, forwards everything else; the raw env is `.env`."""
@@ -395,6 +471,8 @@ REGISTRY = {   # gym_flock/__init__.py:53-63, 90-94
     'Flocking-v0': (FlockingEnv, 1000),
     'FlockingRelative-v0': (FlockingRelativeEnv, 1000),
     'FlockingTwoFlocks-v0': (FlockingTwoFlocksEnv, 500),   # SURVEY.md 8f "next #1": same kernel, different reset
+    'FlockingLeader-v0': (FlockingLeaderEnv, 200),         # gym_flock/__init__.py:65-69
+    'FlockingStochastic-v0': (FlockingStochasticEnv, 500), # gym_flock/__init__.py:84-88
 }
 
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FLOCK_ABI_VERSION 1
+#define FLOCK_ABI_VERSION 2
 
 /* flags */
 #define FLOCK_CENTRALIZED   0x1   /* controller(centralized=True), flocking_relative.py:200-206 */
@@ -63,7 +63,16 @@ typedef struct FlockParams {
                              *   addressed by GLOBAL row but only rows [row_lo,row_hi) are ever touched, so a caller
                              *   may pass shard-sized buffers shifted back by row_lo rows. */
     int32_t lanes;          /* threads cooperating on one row (power of two <= 32); 0 = choose */
-    int32_t reserved;
+    int32_t reserved;       /* 0 (tuning / diagnostics word, see FLOCK_TUNE in gym_flock_b200/_lib.py) */
+    /* ---- flocking variants through the same kernel; all zero = FlockingRelative / Flocking ---- */
+    double  step_scale;     /* step(): a = u * step_scale.  0 = action_scalar (flocking_relative.py:96);
+                             *   1.0 for FlockingLeader (self.u = u, flocking_leader.py:24); 6.0 for FlockingStochastic */
+    double  state_scale;    /* FlockingStochastic: x *= scale before, x /= scale after the Euler step
+                             *   (flocking_stoch.py:18,33); 0 or 1 = none */
+    double  u_clip;         /* FlockingStochastic: clip the action before the step and the controller output to
+                             *   +-u_clip (flocking_stoch.py:16,43); 0 = none */
+    int32_t n_leaders;      /* FlockingLeader: agents [0, n_leaders) are not actuated (flocking_leader.py:11-12,27-31) */
+    int32_t pad_;
 } FlockParams;
 
 int         flock_abi_version(void);

@@ -119,6 +119,17 @@ def load():
     return _cache["classes"]
 
 
+def load_variant(module: str, cls: str):
+    """Load another class of the reference's flocking package (e.g. 'flocking_leader', 'FlockingLeaderEnv')."""
+    load()
+    root = reference_root()
+    for dep in ("utils", module):
+        name = f"gym_flock.envs.flocking.{dep}"
+        if name not in sys.modules:
+            _exec(os.path.join(root, "gym_flock/envs/flocking", dep + ".py"), name)
+    return getattr(sys.modules[f"gym_flock.envs.flocking.{module}"], cls)
+
+
 class CfgSection(dict):
     """Minimal configparser-section look-alike for params_from_cfg (flocking_relative.py:68-85)."""
 

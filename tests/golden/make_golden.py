@@ -87,7 +87,39 @@ def smoke_seed0():
     return out
 
 
+def run_variant(which, n, seed):
+    """FlockingLeader-v0 / FlockingStochastic-v0 of the reference, state injected, 200-step expert rollout."""
+    if which == "leader":
+        env = ref_loader.load_variant("flocking_leader", "FlockingLeaderEnv")()
+    else:
+        env = ref_loader.load_variant("flocking_stoch", "FlockingStochasticEnv")()
+    x0 = initial_state(n, seed=seed, min_dist=0.1)
+    env.n_agents = n
+    if which == "leader":
+        env.mask = np.ones((n,)); env.mask[0:env.n_leaders] = 0
+        x0[0:env.n_leaders, 2:4] = 1.75
+    env.x = x0.copy()
+    env.compute_helpers()
+    out = {"x0": x0.copy(), "values_0": env.state_values.copy(), "u_0": env.controller()}
+    np.random.seed(seed)
+    rewards, dts = np.zeros(STEPS), np.zeros(STEPS)
+    for t in range(1, STEPS + 1):
+        u = env.controller()
+        (values, net), r, done, info = env.step(u)
+        rewards[t - 1], dts[t - 1] = r, env.dt
+        if t in RECORD:
+            out[f"x_{t}"] = env.x.copy(); out[f"u_{t}"] = u.copy(); out[f"values_{t}"] = values.copy()
+            out[f"adj_{t}"] = np.packbits(env.adj_mat.astype(np.uint8), axis=1)
+    out["rewards"], out["dts"] = rewards, dts
+    out["adj_mean_200"] = env.adj_mat_mean.copy()
+    out["meta"] = np.array([n, seed])
+    return out
+
+
 def main():
+    for which, n, seed in (("leader", 100, 31), ("stochastic", 100, 32), ("leader", 20, 33), ("stochastic", 33, 34)):
+        np.savez_compressed(os.path.join(HERE, f"variant_{which}_n{n}.npz"), **run_variant(which, n, seed))
+        print("wrote variant", which, n)
     for name, kind, n, cen, cr, dt, seed, md in CASES:
         x0 = initial_state(n, seed=seed, min_dist=md)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(kind, n, cen, cr, dt, x0))

@@ -26,13 +26,14 @@ def test_every_declared_symbol_is_exported(L):
             "flock_ctx_step", "flock_ctx_controller", "flock_last_error"} <= names
     for n in sorted(names):
         assert hasattr(L, n), n
-    assert L.flock_abi_version() == 1
+    assert L.flock_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():
     from gym_flock_b200._lib import FlockParams
-    assert ctypes.sizeof(FlockParams) == 64
+    assert ctypes.sizeof(FlockParams) == 96
     assert FlockParams.comm_radius.offset == 8 and FlockParams.flags.offset == 40 and FlockParams.lanes.offset == 56
+    assert FlockParams.step_scale.offset == 64 and FlockParams.n_leaders.offset == 88
 
 
 def test_argument_validation_needs_no_gpu(L):
@@ -89,7 +90,8 @@ def test_drop_in_surface_and_synthetic_states():
                           nx_system=4, n_features=6, nu=2, mean_pooling=True, centralized=True).items():
         assert getattr(env, attr) == val
     assert abs(env.comm_radius2 - 0.81) < 1e-15 and isinstance(env.seed(5), list)
-    assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0", "FlockingTwoFlocks-v0"}
+    assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0", "FlockingTwoFlocks-v0", "FlockingLeader-v0",
+                                        "FlockingStochastic-v0"}
     with pytest.raises(KeyError):
         gf.make("Shepherding-v0")
     a, b = initial_state(50, seed=7, min_dist=0.1), initial_states(2, 50, seed=7, min_dist=0.1)

@@ -149,3 +149,37 @@ def test_two_flocks_variant_runs_and_matches_oracle():
     ref = c_oracle.rollout(x0, 5)
     assert np.array_equal(env.env.x, ref["x"]) and np.array_equal(values, ref["values"]) and np.array_equal(net, ref["adj_mean"])
     env.close()
+
+
+@pytest.mark.parametrize("name", ["variant_leader_n100", "variant_leader_n20", "variant_stochastic_n100",
+                                  "variant_stochastic_n33"])
+def test_leader_and_stochastic_variants_match_reference_golden(name, monkeypatch):
+    """FlockingLeader-v0 / FlockingStochastic-v0 through the same kernel (FlockParams.n_leaders / step_scale /
+    state_scale / u_clip), bit-exact against the reference's own rollouts (committed goldens)."""
+    import gym_flock_b200 as gf
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n = int(g["meta"][0])
+    leader = "leader" in name
+    env = (gf.FlockingLeaderEnv if leader else gf.FlockingStochasticEnv)()
+    env.n_agents = n
+    if leader:
+        env.mask = np.ones((n,)); env.mask[0:env.n_leaders] = 0
+    else:
+        dts = iter(g["dts"].tolist())
+        monkeypatch.setattr(np.random, "normal", lambda *a, **k: next(dts))   # the reference's draws, replayed
+    env.set_state(g["x0"])
+    assert np.array_equal(env.state_values, g["values_0"])
+    assert np.array_equal(env.controller(), g["u_0"])
+    rewards = np.zeros(200)
+    for t in range(1, 201):
+        u = env.controller()
+        (values, net), r, done, info = env.step(u)
+        rewards[t - 1] = r
+        if t in (1, 2, 50, 100, 200):
+            assert np.array_equal(env.x, g[f"x_{t}"]), t
+            assert np.array_equal(u, g[f"u_{t}"]), t
+            assert np.array_equal(values, g[f"values_{t}"]), t
+            assert np.array_equal((net > 0).astype(np.uint8), np.unpackbits(g[f"adj_{t}"], axis=1)[:, :n]), t
+    assert np.array_equal(rewards, g["rewards"])
+    assert np.array_equal(net, g["adj_mean_200"])
+    env.close()

@@ -64,3 +64,36 @@ def test_smoke_seed0_golden():
     assert np.array_equal(h["values"], g["values_0"]) and np.array_equal(h["adj_mean"], g["adj_mean_0"])
     deg = (h["adj"].sum(1))
     assert (deg.min(), deg.max()) == (2.0, 11.0) and abs(deg.mean() - 6.84) < 1e-12
+
+
+import glob, os
+from golden_util import GOLDEN_DIR
+
+
+def _variant_files():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "variant_*.npz")))
+
+
+@pytest.mark.parametrize("name", _variant_files())
+def test_numpy_port_variants_match_reference_golden(name):
+    """FlockingLeader-v0 / FlockingStochastic-v0: the restated step variants reproduce the reference bit for bit."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    leader = "leader" in name
+    x = g["x0"].copy()
+    h = fnp.compute_helpers(x, 0.81)
+    assert np.array_equal(h["values"], g["values_0"])
+    rewards = np.zeros(200)
+    for t in range(1, 201):
+        u = fnp.controller(h, 0.9, True)
+        if leader:
+            x = fnp.integrate_leader(x, u, 0.01, 2)
+        else:
+            u = np.clip(u, -0.5, 0.5)                                   # flocking_stoch.py:43
+            x = fnp.integrate_stochastic(x, u, float(g["dts"][t - 1]))
+        h = fnp.compute_helpers(x, 0.9 * 0.9)
+        rewards[t - 1] = fnp.instant_cost(x)
+        if t in RECORD:
+            assert np.array_equal(x, g[f"x_{t}"]), t
+            assert np.array_equal(u, g[f"u_{t}"]), t
+            assert np.array_equal(h["values"], g[f"values_{t}"]), t
+    assert np.array_equal(rewards, g["rewards"])
