@@ -39,6 +39,12 @@ template <> struct Tr<double> {
         y = fma(y, e, y);
         return y;
     }
+    static __device__ __forceinline__ double rcp1(double x) {   // seed (2^-23) + ONE Newton step: ~2^-46
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        const double e = fma(-x, y, 1.0);
+        return fma(y, e, y);
+    }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }

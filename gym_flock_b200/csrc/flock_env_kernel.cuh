@@ -61,7 +61,7 @@ struct KArgs {
     StepVariant var;     // flocking variants (leader / stochastic); defaults reproduce FlockingRelative
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
-    unsigned off_xs, off_pf, off_masks, off_stats, off_zero;
+    unsigned off_xs, off_pf, off_masks, off_stats, off_zero, off_idg;
     int out_mode; // dense adjacency output: 0 = bulk zero-fill + scatter of the non-zeros; 1 = in-warp row expansion
     int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
 };
@@ -77,6 +77,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// one agent's state from shared memory by 32-bit shared address (two LDS.128, no generic-address arithmetic)
+__device__ __forceinline__ double4 lds_state(const unsigned saddr) {
+    double4 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+16];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "r"(saddr));
+    return v;
+}
 
 // shared-memory double accumulate (a handful per env and CTA; CAS loop is fine)
 __device__ __forceinline__ void smem_add(double *p, double v) { atomicAdd(p, v); }
@@ -141,6 +149,8 @@ __device__ __forceinline__ bool refine_exact(const double4 xi, const double4 xj,
 
 // Fast refine (fp64, fused): one reciprocal instead of four divides.  Candidates are a superset (conservative fp32
 // filter, possibly an inflated kNN radius), so pairs beyond both radii leave early.
+// NEWTON1 (fp32 output mode): one Newton step on the 2^-23 seed (relative error ~2^-46, far below float rounding).
+template <bool NEWTON1 = false>
 __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, const double R2, const double Rm,
                                             Acc &A) {
     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
@@ -148,7 +158,7 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
     const bool a = r2 < R2;
     const bool g = r2 <= Rm;
     if (a || g) {
-        const double inv2 = Tr<double>::rcp(r2);
+        const double inv2 = NEWTON1 ? Tr<double>::rcp1(r2) : Tr<double>::rcp(r2);
         if (a) {
             const double inv4 = inv2 * inv2;
             A.f0 += xi.z - xj.z; A.f3 += xi.w - xj.w;
@@ -166,75 +176,69 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
 // ---- in-warp expansion of the warp's rows of adj_mean (small rows) -----------------------------------------------
 // The warp's rows are consecutive rows of the [E*N, N] output.  A row is cut into nv = N/V groups of V elements
 // (16 bytes when V is maximal); a lane owns one group column (and, when rows are short, one of RPI rows handled per
-// iteration), so its mask word index and shift are loop invariants: per iteration one LDS, one SHFL (1/deg of the
-// row) and one coalesced streaming store.  No partial sectors, nothing to wait for.
+// iteration), so its mask word and shift are loop invariants.  Mask words are stored word-major ([word][thread]) and
+// 1/deg of every row sits in shared memory, so in the unrolled loop both loads use immediate offsets: per row two LDS,
+// the bit -> value selects and one predicated, coalesced streaming store.  No partial sectors, nothing to wait for.
 template <typename TO, int V>
-__device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wmasks, const int W, const int N, const int nrows,
-                                            const TO idg, const int lane) {
+__device__ __forceinline__ void store_group(TO *dst, const unsigned bits, const TO v, const bool on) {
+    const unsigned p = on ? 1u : 0u;
+    if constexpr (sizeof(TO) == 4 && V == 4) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                     :: "l"(dst), "f"((bits & 1u) ? v : 0.f), "f"((bits & 2u) ? v : 0.f), "f"((bits & 4u) ? v : 0.f),
+                        "f"((bits & 8u) ? v : 0.f), "r"(p) : "memory");
+    } else if constexpr (sizeof(TO) == 4 && V == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.cs.v2.f32 [%0], {%1, %2};\n\t}"
+                     :: "l"(dst), "f"((bits & 1u) ? v : 0.f), "f"((bits & 2u) ? v : 0.f), "r"(p) : "memory");
+    } else if constexpr (sizeof(TO) == 8 && V == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.cs.v2.f64 [%0], {%1, %2};\n\t}"
+                     :: "l"(dst), "d"((bits & 1u) ? v : 0.0), "d"((bits & 2u) ? v : 0.0), "r"(p) : "memory");
+    } else {
+        if (on) __stcs(dst, (bits & 1u) ? v : TO(0));
+    }
+}
+
+// wm: mask word 0 of the warp's first row (word q of row r at wm[q * MS + r]); idgs: 1/deg of the warp's rows
+template <typename TO, int V>
+__device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const int MS, const TO *idgs, const int N,
+                                            const int nrows, const int lane) {
     const int nv = N / V;                               // groups per row
     const int passes = (nv + 31) >> 5;                  // > 1 when a row has more than 32 groups
     const int rpi = (nv >= 32) ? 1 : 32 / nv;           // rows per iteration when rows are short
     const int sr = (nv >= 32) ? 0 : lane / nv;          // this lane's sub-row within an iteration
     const int cv0 = (nv >= 32) ? lane : lane - sr * nv; // this lane's group column (first pass)
     const bool lane_on = (nv >= 32) || (sr < rpi);
-    auto emit = [&](const int rr, const int cv, const TO v) {
-        const int c = cv * V;                           // first column of the group
-        const unsigned bits = wmasks[(size_t)rr * W + (c >> 5)] >> (c & 31);
-        TO *dst = wout + (size_t)rr * N + c;
-        if constexpr (sizeof(TO) == 4 && V == 4) {
-            __stcs(reinterpret_cast<float4 *>(dst),
-                   make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
-        } else if constexpr (sizeof(TO) == 4 && V == 2) {
-            __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
-        } else if constexpr (sizeof(TO) == 8 && V == 2) {
-            __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
-        } else {
-            __stcs(dst, (bits & 1u) ? v : TO(0));
-        }
-    };
-    auto put = [&](TO *dst, const unsigned bits, const TO v) {
-        if constexpr (sizeof(TO) == 4 && V == 4) {
-            __stcs(reinterpret_cast<float4 *>(dst),
-                   make_float4((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f, (bits & 4u) ? v : 0.f, (bits & 8u) ? v : 0.f));
-        } else if constexpr (sizeof(TO) == 4 && V == 2) {
-            __stcs(reinterpret_cast<float2 *>(dst), make_float2((bits & 1u) ? v : 0.f, (bits & 2u) ? v : 0.f));
-        } else if constexpr (sizeof(TO) == 8 && V == 2) {
-            __stcs(reinterpret_cast<double2 *>(dst), make_double2((bits & 1u) ? v : 0.0, (bits & 2u) ? v : 0.0));
-        } else {
-            __stcs(dst, (bits & 1u) ? v : TO(0));
-        }
-    };
     if (passes == 1 && rpi == 1 && nrows == 32) {       // a full warp of rows, one row per iteration: fixed trip count
         const bool on = lane < nv;
         const int c = on ? lane * V : 0;
         const int sh = c & 31;
-        const unsigned *mp = wmasks + (c >> 5);
+        const unsigned *mp = wm + (c >> 5) * MS;
         TO *dst = wout + c;
-#pragma unroll 8
+#pragma unroll
         for (int r = 0; r < 32; ++r) {
-            const TO v = __shfl_sync(0xffffffffu, idg, r);     // 1/deg of row r (held by lane r)
-            if (on) put(dst, *mp >> sh, v);
-            mp += W; dst += N;
+            store_group<TO, V>(dst, mp[r] >> sh, idgs[r], on);
+            dst += N;
         }
     } else if (passes == 1) {                           // short rows (several per iteration) or a partial warp
-        // loop invariants per lane: mask word / shift of its group column; pointers advance by rpi rows per iteration
         const bool on = lane_on && cv0 < nv;
-        const int c = cv0 * V;
+        const int c = on ? cv0 * V : 0;
         const int sh = c & 31;
-        const unsigned *mp = wmasks + sr * W + (c >> 5);
-        TO *dst = wout + (size_t)sr * N + c;
-        const int mstep = rpi * W;
+        const unsigned *mp = wm + (c >> 5) * MS + (on ? sr : 0);
+        const TO *ip = idgs + (on ? sr : 0);
+        TO *dst = wout + (size_t)(on ? sr : 0) * N + c;
         const size_t dstep = (size_t)rpi * N;
         const int last = nrows - sr;                    // this lane stores while r < last
         for (int r = 0; r < nrows; r += rpi) {
-            const TO v = __shfl_sync(0xffffffffu, idg, (r + sr) & 31);
-            if (on && r < last) put(dst, *mp >> sh, v);
-            mp += mstep; dst += dstep;
+            const bool go = on && r < last;
+            store_group<TO, V>(dst, go ? (mp[r] >> sh) : 0u, go ? ip[r] : TO(0), go);
+            dst += dstep;
         }
     } else {
         for (int r = 0; r < nrows; ++r) {
-            const TO v = __shfl_sync(0xffffffffu, idg, r);
-            for (int cv = lane; cv < nv; cv += 32) emit(r, cv, v);
+            const TO v = idgs[r];
+            for (int cv = lane; cv < nv; cv += 32) {
+                const int c = cv * V;
+                store_group<TO, V>(wout + (size_t)r * N + c, wm[(c >> 5) * MS + r] >> (c & 31), v, true);
+            }
         }
     }
 }
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     const bool cen = a.centralized != 0;
     const double4 *xe = xs + g * N;
     const double4 xi = xe[i];
-    unsigned *mrow = masks + (size_t)tid * a.W;
+    unsigned *mrow = masks + tid;                           // word-major: word w of this thread at mrow[w * nthr]
     const size_t grow = (size_t)env * N + i;                // global row (agent) index
 
     // ---- per-warp bulk zero-fill of the warp's rows of the dense adjacency ---------------------------------------
@@ -420,28 +424,50 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
         // |p_j|inf <= |p_i|inf + rc (rc = sqrt(thrC)); each coordinate is rounded to <= |p|*2^-24, so
         // |d(dx)| <= (2|p_i|inf + 3rc)*2^-24 and |d(r2)| <= 4 rc |d(dx)| + a few ulp(r2).
         const float tc = (float)a.thrC, rc = sqrtf(tc);
-        const float thrA = tc * (1.0f + 2e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+        const float thrA = tc * (1.0f + 3e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+        const float2 nthr2 = make_float2(-thrA, -thrA);
         for (int w = 0; w * 16 < ((a.tune & 8) ? 0 : nslots); ++w) {
             unsigned bits = 0;
             const int tbase = w * 16;
             const int tend = min(16, nslots - tbase);
-            auto body = [&](const int tt) {
-                const int m = sub + LANES * (tbase + tt);
-                const float4 q = pe[m];
-                const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
-                const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
-                const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-                bits |= (r2.x <= thrA) ? (1u << (2 * tt)) : 0u;
-                bits |= (r2.y <= thrA) ? (2u << (2 * tt)) : 0u;
-                if constexpr (KNN) { top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1); }
-            };
-            if (tend == 16) {
+            if constexpr (KNN) {
+                auto body = [&](const int tt) {
+                    const int m = sub + LANES * (tbase + tt);
+                    const float4 q = pe[m];
+                    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                    const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                    const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+                    bits |= (r2.x < thrA) ? (1u << (2 * tt)) : 0u;
+                    bits |= (r2.y < thrA) ? (2u << (2 * tt)) : 0u;
+                    top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1);
+                };
+                if (tend == 16) {
 #pragma unroll
-                for (int tt = 0; tt < 16; ++tt) body(tt);
+                    for (int tt = 0; tt < 16; ++tt) body(tt);
+                } else {
+                    for (int tt = 0; tt < tend; ++tt) body(tt);
+                }
             } else {
-                for (int tt = 0; tt < tend; ++tt) body(tt);
+                // s = dx^2 + (dy^2 - thrA): the candidate test is the SIGN of s (two packed FFMA2, no compare); one
+                // funnel shift per pair moves it into the word (first pair ends up highest: one BREV per word)
+                auto body = [&](const int tt) {
+                    const float4 q = pe[sub + LANES * (tbase + tt)];
+                    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                    const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                    const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
+                    bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
+                    bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+                };
+                if (tend == 16) {
+#pragma unroll
+                    for (int tt = 0; tt < 16; ++tt) body(tt);
+                    bits = __brev(bits);
+                } else {
+                    for (int tt = 0; tt < tend; ++tt) body(tt);
+                    bits = __brev(bits) >> (32 - 2 * tend);          // 0 < tend < 16
+                }
             }
-            mrow[w] = bits;
+            mrow[w * nthr] = bits;
             cnt += __popc(bits);
         }
     } else {
@@ -478,7 +504,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
             } else {
                 for (int kk = 0; kk < kend; ++kk) body(kk);
             }
-            mrow[w] = bits;
+            mrow[w * nthr] = bits;
             cnt += __popc(bits);
         }
     }
@@ -533,31 +559,37 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     // One flat loop per lane; the advance to the next word is straight-line code inside the loop body, so a warp
     // iterates ~max-over-lanes(total candidates) times.
     int deg = 0;
+    const double R2r = a.R2, Rmr = a.Rm;
     if (!(a.tune & 4)) {
         // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
         {
             int kd = -1;
             if constexpr (PA32) { if (valid && ((i >> 1) % LANES) == sub) kd = 2 * ((i >> 1) / LANES) + (i & 1); }
             else { if (valid && (i % LANES) == sub) kd = i / LANES; }
-            if (kd >= 0) { mrow[kd >> 5] &= ~(1u << (kd & 31)); --cnt; }
+            if (kd >= 0) { mrow[(kd >> 5) * nthr] &= ~(1u << (kd & 31)); --cnt; }
         }
         int w = 0;
         unsigned cand = nw > 0 ? mrow[0] : 0u, ex = 0;
+        const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe);   // 32-bit shared address: stays in a register
         for (int c = 0; c < cnt; ++c) {                     // counted loop: cnt candidates are known to exist
             while (cand == 0) {                             // word exhausted: publish its exact bits, fetch the next
-                mrow[w] = ex; ex = 0;
+                mrow[w * nthr] = ex; deg += __popc(ex); ex = 0;
                 ++w;
-                cand = mrow[w];
+                cand = mrow[w * nthr];
             }
-            const int k = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const double4 xj = xe[j_of(w * 32 + k)];
+            const unsigned low = cand & (0u - cand);        // lowest candidate bit
+            cand ^= low;
+            const int k = 31 - __clz((int)low);
+            int j;
+            if constexpr (LANES == 1) j = w * 32 + k;       // one thread per row: bit position == agent index
+            else j = j_of(w * 32 + k);
+            const double4 xj = lds_state(xe_s + (unsigned)j * 32u);
             bool adj;
             if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
-            else adj = refine_fast(xi, xj, a.R2, a.Rm, A);
-            if (adj) { ex |= 1u << k; ++deg; }
+            else adj = refine_fast<PA32>(xi, xj, R2r, Rmr, A);
+            if (adj) ex |= low;
         }
-        if (nw > 0) mrow[w] = ex;                           // words after w held no candidates: already zero
+        if (nw > 0) { mrow[w * nthr] = ex; deg += __popc(ex); }    // words after w held no candidates: already zero
     }
 
     // ---- reduce across the LANES threads of a row ----------------------------------------------------------
@@ -614,16 +646,19 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     if (a.out_mode == 1) {
         // small rows: expand the warp's 32 rows from their exact bit masks (LANES == 1, full rows; host guarantees it)
         if constexpr (LANES == 1) {
-            __syncwarp();                                    // the lanes' mask words (shared memory) are complete
+            TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
+            idg_s[tid] = idg;
+            __syncwarp();                                    // the lanes' mask words and 1/deg (shared memory) are complete
             const int wr0 = r0 + (tid - lane);               // first flat row of this warp == its global row (nre == N)
             const int nrows = min(32, r1 - wr0);
             if (nrows > 0 && !(a.tune & 2)) {
                 TO *wout = net + (size_t)wr0 * N;
-                const unsigned *wm = masks + (size_t)(tid - lane) * a.W;
+                const unsigned *wm = masks + (tid - lane);
+                const TO *idgs = idg_s + (tid - lane);
                 constexpr int VMAX = 16 / (int)sizeof(TO);
-                if (N % VMAX == 0) expand_rows<TO, VMAX>(wout, wm, a.W, N, nrows, idg, lane);
-                else if (VMAX == 4 && N % 2 == 0) expand_rows<TO, 2>(wout, wm, a.W, N, nrows, idg, lane);
-                else expand_rows<TO, 1>(wout, wm, a.W, N, nrows, idg, lane);
+                if (N % VMAX == 0) expand_rows<TO, VMAX>(wout, wm, nthr, idgs, N, nrows, lane);
+                else if (VMAX == 4 && N % 2 == 0) expand_rows<TO, 2>(wout, wm, nthr, idgs, N, nrows, lane);
+                else expand_rows<TO, 1>(wout, wm, nthr, idgs, N, nrows, lane);
             }
         }
         return;
@@ -638,7 +673,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
         int w = 0;
         unsigned ex = nw > 0 ? mrow[0] : 0u;
         while (w < nw) {
-            if (ex == 0) { ++w; ex = (w < nw) ? mrow[w] : 0u; }
+            if (ex == 0) { ++w; ex = (w < nw) ? mrow[w * nthr] : 0u; }
             if (ex != 0) {
                 const int k = __ffs(ex) - 1;
                 ex &= ex - 1;

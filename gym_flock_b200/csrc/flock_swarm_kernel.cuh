@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
                     top.insert(fma(dx, dx, dy * dy), j);
                 }
-                if (refine_fast(xi, xj, a.R2, a.Rm, A)) {
+                if (refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) {
                     const int pos = atomicAdd(&lcnt[rl], 1);
                     if (pos < a.CAP) lrow[pos] = (unsigned)j;
                 }
