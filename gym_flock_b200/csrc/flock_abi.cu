@@ -107,7 +107,7 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     k.off_pf = align16(size_xs);
     const size_t size_pf = pa32 ? (size_t)GMAX * NP2 * 16 : 0;
     k.off_masks = align16(k.off_pf + size_pf);
-    const size_t size_lists = (size_t)threads * W * 4;
+    const size_t size_lists = (size_t)flock::MS * (W + 1) * 4;     // word-major, fixed stride, one spare word row (prefetch)
     k.off_stats = align16(k.off_masks + size_lists);
     k.off_zero = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);
     k.off_idg = align16((size_t)k.off_zero + flock::ZERO_BYTES);      // 1/deg per row (in-warp row expansion)
@@ -128,6 +128,8 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     // small full rows: expand in the warp (coalesced stores); large rows: bulk zero-fill + scatter
     k.out_mode = (lanes == 1 && nrows == N && (size_t)N * tbytes <= 2048 && !((p->reserved >> 8) & 16)) ? 1 : 0;
     k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
+    k.ulim = 10.0 * k.inv_ascale;
+    if (p->u_clip > 0.0) k.ulim = std::min(k.ulim, p->u_clip);
     pl.lanes = lanes; pl.threads = threads;
     pl.grid = grid;
     return FLOCK_OK;

@@ -58,6 +58,7 @@ struct KArgs {
     int NP2;      // pair slots per env in the packed fp32 position array: (N + 1) / 2
     double R, R2, dt, ascale;
     double inv_ascale;   // 1/ascale (fast modes multiply; EXACT divides)
+    double ulim;         // fast modes: the action clamp after scaling, min(10/ascale, u_clip)
     StepVariant var;     // flocking variants (leader / stochastic); defaults reproduce FlockingRelative
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
@@ -66,6 +67,7 @@ struct KArgs {
     int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
 };
 
+constexpr int MS = FLOCK_MAXT;     // mask words are stored word-major with a fixed stride: word w of thread t at masks[w * MS + t]
 constexpr int ZERO_BYTES = 2048;   // shared zero block: source of the bulk (TMA) zero-fill of the dense adjacency
 
 // ---- bulk async copy (TMA, 1-D) shared -> global ------------------------------------------------------------
@@ -84,6 +86,12 @@ __device__ __forceinline__ double4 lds_state(const unsigned saddr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%4];\n\tld.shared.v2.f64 {%2, %3}, [%4+16];"
                  : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "r"(saddr));
     return v;
+}
+
+__device__ __forceinline__ int bfind(const unsigned v) {        // index of the highest set bit (FLO)
+    int k;
+    asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(v));
+    return k;
 }
 
 // shared-memory double accumulate (a handful per env and CTA; CAS loop is fine)
@@ -173,6 +181,72 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
     return a;
 }
 
+// Fast refine of one candidate as straight-line, branch-free code (the lanes of a warp disagree on almost every
+// condition, and every divergent region costs its BSSY/BSYNC pair and re-issued instructions).  Same arithmetic as
+// refine_fast -- one reciprocal (seed + Newton) instead of four divides, fused multiply-adds, fp64 throughout -- with the
+// two masks applied as exact factors 1.0 / 0.0 (x * 1.0 and + 0.0 are exact, so the sums are bit-identical to the
+// branchy form).  The caller passes a valid agent address even when the lane idles (low == 0): pv masks everything.
+//   !adjacent  : the candidate's bit is cleared in its mask word (shared-memory RED at waddr)
+#define FLOCK_REFINE_PRED_ASM(SECOND_NEWTON_STEP)                                                                  \
+    asm volatile(                                                                                                   \
+        "{\n\t"                                                                                                     \
+        ".reg .pred pv, pa, pg, pr;\n\t"                                                                            \
+        ".reg .b32 nl, hi;\n\t"                                                                                     \
+        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c, ma, mg;\n\t"                      \
+        "setp.ne.u32 pv, %10, 0;\n\t"                                                                               \
+        "ld.shared.v2.f64 {xjx, xjy}, [%11];\n\t"                                                                   \
+        "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t"                                                                \
+        "sub.f64 dx, %13, xjx;\n\t"                                                                                 \
+        "sub.f64 dy, %14, xjy;\n\t"                                                                                 \
+        "mul.f64 r2, dy, dy;\n\t"                                                                                   \
+        "fma.rn.f64 r2, dx, dx, r2;\n\t"                                                                            \
+        "setp.lt.and.f64 pa, r2, %17, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                          \
+        "setp.le.and.f64 pg, r2, %18, pv;\n\t"  /* gradient mask: r2 <= Rm */                                       \
+        "setp.geu.and.f64 pr, r2, %17, pv;\n\t" /* a candidate that is not a neighbour */                           \
+        "selp.b32 hi, 0x3FF00000, 0, pa;\n\t"                                                                       \
+        "mov.b64 ma, {0, hi};\n\t"              /* 1.0 or 0.0 */                                                    \
+        "selp.b32 hi, 0x3FF00000, 0, pg;\n\t"                                                                       \
+        "mov.b64 mg, {0, hi};\n\t"                                                                                  \
+        "rcp.approx.ftz.f64 y, r2;\n\t"                                                                             \
+        "neg.f64 e, r2;\n\t"                                                                                        \
+        "fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\t"                                                               \
+        "fma.rn.f64 y, y, c, y;\n\t"                                                                                \
+        SECOND_NEWTON_STEP                                                                                          \
+        "mul.f64 ya, y, ma;\n\t"                                                                                    \
+        "mul.f64 yg, y, mg;\n\t"                                                                                    \
+        "mul.f64 y4, ya, ya;\n\t"                                                                                   \
+        "sub.f64 dvx, %15, xjz;\n\t"                                                                                \
+        "sub.f64 dvy, %16, xjw;\n\t"                                                                                \
+        "fma.rn.f64 %0, dvx, ma, %0;\n\t"                                                                           \
+        "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                            \
+        "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                            \
+        "fma.rn.f64 %3, dvy, ma, %3;\n\t"                                                                           \
+        "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                            \
+        "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                            \
+        "neg.f64 c, yg;\n\t"                                                                                        \
+        "fma.rn.f64 c, c, yg, yg;\n\t" /* 1/r2 - 1/r4 */                                                            \
+        "fma.rn.f64 %6, dx, c, %6;\n\t"                                                                             \
+        "fma.rn.f64 %7, dy, c, %7;\n\t"                                                                             \
+        "@pa add.s32 %8, %8, 1;\n\t"                                                                                \
+        "@pv add.s32 %9, %9, -1;\n\t"                                                                               \
+        "not.b32 nl, %10;\n\t"                                                                                      \
+        "@pr red.shared.and.b32 [%12], nl;\n\t"                                                                     \
+        "}"                                                                                                         \
+        : "+d"(A.f0), "+d"(A.f1), "+d"(A.f2), "+d"(A.f3), "+d"(A.f4), "+d"(A.f5), "+d"(A.gx), "+d"(A.gy), "+r"(deg),  \
+          "+r"(left)                                                                                                \
+        : "r"(low), "r"(xaddr), "r"(waddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm)            \
+        : "memory")
+
+template <bool NEWTON1>
+__device__ __forceinline__ void refine_fast_pred(const double4 xi, const unsigned xaddr, const unsigned low, const unsigned waddr,
+                                                 const double R2, const double Rm, Acc &A, int &deg, int &left) {
+    if constexpr (NEWTON1) {            // fp32 output mode: seed (2^-23) + one Newton step
+        FLOCK_REFINE_PRED_ASM("");
+    } else {                            // fp64 output mode: two Newton steps (full double accuracy)
+        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t");
+    }
+}
+
 // ---- in-warp expansion of the warp's rows of adj_mean (small rows) -----------------------------------------------
 // The warp's rows are consecutive rows of the [E*N, N] output.  A row is cut into nv = N/V groups of V elements
 // (16 bytes when V is maximal); a lane owns one group column (and, when rows are short, one of RPI rows handled per
@@ -199,15 +273,10 @@ __device__ __forceinline__ void store_group(TO *dst, const unsigned bits, const 
 
 // wm: mask word 0 of the warp's first row (word q of row r at wm[q * MS + r]); idgs: 1/deg of the warp's rows
 template <typename TO, int V>
-__device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const int MS, const TO *idgs, const int N,
+__device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const TO *idgs, const int N,
                                             const int nrows, const int lane) {
     const int nv = N / V;                               // groups per row
-    const int passes = (nv + 31) >> 5;                  // > 1 when a row has more than 32 groups
-    const int rpi = (nv >= 32) ? 1 : 32 / nv;           // rows per iteration when rows are short
-    const int sr = (nv >= 32) ? 0 : lane / nv;          // this lane's sub-row within an iteration
-    const int cv0 = (nv >= 32) ? lane : lane - sr * nv; // this lane's group column (first pass)
-    const bool lane_on = (nv >= 32) || (sr < rpi);
-    if (passes == 1 && rpi == 1 && nrows == 32) {       // a full warp of rows, one row per iteration: fixed trip count
+    if (nv > 16 && nv <= 32 && nrows == 32) {           // a full warp of rows, one row per iteration: fixed trip count
         const bool on = lane < nv;
         const int c = on ? lane * V : 0;
         const int sh = c & 31;
@@ -218,7 +287,14 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const 
             store_group<TO, V>(dst, mp[r] >> sh, idgs[r], on);
             dst += N;
         }
-    } else if (passes == 1) {                           // short rows (several per iteration) or a partial warp
+        return;
+    }
+    const int passes = (nv + 31) >> 5;                  // > 1 when a row has more than 32 groups
+    const int rpi = (nv >= 32) ? 1 : 32 / nv;           // rows per iteration when rows are short
+    const int sr = (nv >= 32) ? 0 : lane / nv;          // this lane's sub-row within an iteration
+    const int cv0 = (nv >= 32) ? lane : lane - sr * nv; // this lane's group column (first pass)
+    const bool lane_on = (nv >= 32) || (sr < rpi);
+    if (passes == 1) {                                  // short rows (several per iteration) or a partial warp
         const bool on = lane_on && cv0 < nv;
         const int c = on ? cv0 * V : 0;
         const int sh = c & 31;
@@ -243,44 +319,51 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const 
     }
 }
 
-// Resident-CTA targets: the fast kernels are latency bound (divergent refine loops), so occupancy matters more than
-// registers: 256-thread bound, 6 CTAs (48 warps) per SM -> <= 40 registers.  EXACT keeps its registers.
-template <typename TO, int LANES, bool EXACT, bool KNN>
-__global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
-    constexpr bool PA32 = std::is_same<TO, float>::value;   // phase A on packed fp32 positions
-    using TK = typename std::conditional<PA32, float, double>::type;
-    static_assert(!EXACT || (!PA32 && LANES == 1), "EXACT is fp64, one thread per row");
+// ---- one window of rows: [r0, r1) of the flat [E x rows] space and the envs [e0, e0 + nenv) it touches ---------------
+struct Win { int r0, r1, e0, nenv; };
 
-    extern __shared__ __align__(16) unsigned char smem[];
-    double4 *xs = reinterpret_cast<double4 *>(smem + a.off_xs);
-    float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf);       // (px_2m, px_2m+1, py_2m, py_2m+1) - env origin
-    unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);
-    double *stats = reinterpret_cast<double *>(smem + a.off_stats);
-
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31;
-    const int N = a.N;
-    const int nre = a.row_hi - a.row_lo;                    // rows per env handled by this call
-    // ---- the CTA's window of flat rows [r0, r1) and the envs [e0, e0 + nenv) it touches -------------------
-    int r0, r1;
+__device__ __forceinline__ Win window_of(const KArgs &a, const int w) {
+    const int nre = a.row_hi - a.row_lo;
+    Win W;
     if (a.tiles > 0) {
-        const int e = blockIdx.x / a.tiles, t = blockIdx.x - e * a.tiles;
-        r0 = e * nre + t * a.RT;
-        r1 = min(r0 + a.RT, (e + 1) * nre);
+        const int e = w / a.tiles, t = w - e * a.tiles;
+        W.r0 = e * nre + t * a.RT;
+        W.r1 = min(W.r0 + a.RT, (e + 1) * nre);
     } else {
-        r0 = blockIdx.x * a.RT;
-        r1 = min(r0 + a.RT, a.E * nre);
+        W.r0 = w * a.RT;
+        W.r1 = min(W.r0 + a.RT, a.E * nre);
     }
-    const int e0 = r0 / nre;
-    const int nenv = (r1 - 1) / nre - e0 + 1;
-    const float inv_n = 1.0f / (float)N, inv_nre = 1.0f / (float)nre;
-    TO *net = reinterpret_cast<TO *>(a.network);
-    TO *reward = reinterpret_cast<TO *>(a.reward);
+    W.e0 = W.r0 / nre;
+    W.nenv = (W.r1 - 1) / nre - W.e0 + 1;
+    return W;
+}
+
+// the locals every phase of a window uses (unused ones cost nothing)
+#define FLOCK_WIN_LOCALS                                                                                         \
+    constexpr bool PA32 = std::is_same<TO, float>::value; /* phase A on packed fp32 positions */                \
+    [[maybe_unused]] double4 *xs = reinterpret_cast<double4 *>(smem + a.off_xs);                                  \
+    [[maybe_unused]] float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf); /* (px_2m, px_2m+1, py_2m, py_2m+1) - env origin */ \
+    [[maybe_unused]] double *stats = reinterpret_cast<double *>(smem + a.off_stats);                              \
+    [[maybe_unused]] const int tid = threadIdx.x, nthr = blockDim.x;                                              \
+    [[maybe_unused]] const int lane = tid & 31;                                                                   \
+    [[maybe_unused]] const int N = a.N;                                                                           \
+    [[maybe_unused]] const int nre = a.row_hi - a.row_lo; /* rows per env handled by this call */                 \
+    [[maybe_unused]] const int r0 = win.r0, r1 = win.r1, e0 = win.e0, nenv = win.nenv;                            \
+    [[maybe_unused]] const float inv_n = 1.0f / (float)N, inv_nre = 1.0f / (float)nre;                            \
+    [[maybe_unused]] TO *net = reinterpret_cast<TO *>(a.network);                                                 \
+    [[maybe_unused]] TO *reward = reinterpret_cast<TO *>(a.reward);
+
+// ---- phase 0 (all threads; the caller follows it with a block barrier): load, integrate, publish x', stage ---------
+template <typename TO, bool EXACT>
+__device__ __forceinline__ void stage_window(const KArgs &a, unsigned char *smem, const Win win) {
+    FLOCK_WIN_LOCALS
 
     // ---- zero block for the bulk fill, stats flags ------------------------------------------------------------
     {
-        float4 *zb = reinterpret_cast<float4 *>(smem + a.off_zero);
-        for (int q = tid; q < ZERO_BYTES / 16; q += nthr) zb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.out_mode == 0) {
+            float4 *zb = reinterpret_cast<float4 *>(smem + a.off_zero);
+            for (int q = tid; q < ZERO_BYTES / 16; q += nthr) zb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if constexpr (!EXACT) for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
         fence_async_smem();      // generic-proxy zeros -> visible to the async proxy (TMA) after the barrier
     }
@@ -289,33 +372,57 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     {
         const int nag = nenv * N;
         const size_t a0 = (size_t)e0 * N;
-        for (int idx = tid; idx < nag; idx += nthr) {
+        // the plain step (FlockingRelative / Flocking) keeps the loop body short; the variants take the general path
+        const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
+        struct Ag { double4 x; double2 u, ref; int ge, j; };
+        // all loads first (state, action, the env's origin) ...
+        auto fetch = [&](const int idx, Ag &g) {
             const size_t ga = a0 + idx;
-            double4 x = ld_state(a.x_in + ga * 4);
+            g.ge = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;              // exact: idx < 2^20
+            g.j = idx - g.ge * N;
+            g.x = ld_state(a.x_in + ga * 4);
+            g.u = make_double2(0.0, 0.0);
+            if (a.u_in) g.u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + ga);
+            g.ref = make_double2(0.0, 0.0);
+            if constexpr (PA32) g.ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (a0 + (size_t)g.ge * N) * 4));
+        };
+        // ... then the arithmetic and the stores
+        auto finish = [&](const int idx, Ag &g) {
+            const size_t ga = a0 + idx;
+            double4 x = g.x;
+            const int ge = g.ge, j = g.j;
             if (a.u_in) {
-                const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + ga);
-                const int gq = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;
-                x = integrate_variant(x, u, idx - gq * N, a.dt, a.var);
+                if (plain) x = integrate_exact(x, g.u, a.dt, a.var.step_scale);
+                else x = integrate_variant(x, g.u, j, a.dt, a.var);
             }
-            const int ge = (nenv > 1) ? (int)(((float)idx + 0.5f) * inv_n) : 0;     // exact: idx < 2^20
-            const int j = idx - ge * N;
             // every agent's new state is published exactly once: by the CTA that owns local row (j mod rows-per-env)
             // of its env (with full rows that is simply the CTA owning agent j's row)
             const int frj = (e0 + ge) * nre + ((nre == N) ? j : j % nre);
             if (a.x_out && frj >= r0 && frj < r1) st_state(a.x_out + ga * 4, x);
             xs[idx] = x;
             if constexpr (PA32) {
-                const double2 ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (a0 + (size_t)ge * N) * 4));
                 float *p = reinterpret_cast<float *>(pf + (size_t)ge * a.NP2 + (j >> 1));   // origin: agent 0 before the step
-                p[j & 1] = (float)(x.x - ref.x); p[2 + (j & 1)] = (float)(x.y - ref.y);
+                p[j & 1] = (float)(x.x - g.ref.x); p[2 + (j & 1)] = (float)(x.y - g.ref.y);
                 if ((N & 1) && j == N - 1) { p[1] = CUDART_INF_F; p[3] = CUDART_INF_F; }   // odd N: pad slot at infinity
             }
+        };
+        // two agents per thread and iteration: both loads are in flight before the first use
+        for (int idx = tid; idx < nag; idx += 2 * nthr) {
+            const int idx1 = idx + nthr;
+            const bool two = idx1 < nag;
+            Ag g0, g1;
+            fetch(idx, g0);
+            if (two) fetch(idx1, g1);
+            finish(idx, g0);
+            if (two) finish(idx1, g1);
         }
     }
-    __syncthreads();
-    // ==== from here on warps are independent ======================================================================
+}
 
-    // ---- per-env velocity sums (alignment trick) and rewards: one warp per env, published through a flag ------------
+// ---- per-env velocity sums (alignment trick) and rewards: one warp per env, published through a flag ----------------
+template <typename TO, bool EXACT>
+__device__ __forceinline__ void window_stats(const KArgs &a, unsigned char *smem, const Win win) {
+    FLOCK_WIN_LOCALS
     {
         const int warp = tid >> 5, nwarps = nthr >> 5;
         for (int ge = warp; ge < nenv; ge += nwarps) {
@@ -358,6 +465,15 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
         }
     }
 
+}
+
+// ---- the rows of a window: filter, (kNN,) refine, row epilogue; leaves the exact adjacency bits in `masks` and
+//      (small full rows, out_mode 1) 1/deg in `idg_s` for expand_window(); out_mode 0 scatters into the zero-filled rows.
+//      From here on warps are independent.
+template <typename TO, int LANES, bool EXACT, bool KNN>
+__device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem, unsigned *masks, TO *idg_s, const Win win) {
+    FLOCK_WIN_LOCALS
+    using TK = typename std::conditional<PA32, float, double>::type;
     // ---- row assignment -----------------------------------------------------------------------------------
     const int rl = tid / LANES, sub = tid % LANES;
     const int fr = r0 + rl;                                 // flat row
@@ -369,7 +485,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     const bool cen = a.centralized != 0;
     const double4 *xe = xs + g * N;
     const double4 xi = xe[i];
-    unsigned *mrow = masks + tid;                           // word-major: word w of this thread at mrow[w * nthr]
+    unsigned *mrow = masks + tid;                           // word-major: word w of this thread at mrow[w * MS]
     const size_t grow = (size_t)env * N + i;                // global row (agent) index
 
     // ---- per-warp bulk zero-fill of the warp's rows of the dense adjacency ---------------------------------------
@@ -467,7 +583,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
                     bits = __brev(bits) >> (32 - 2 * tend);          // 0 < tend < 16
                 }
             }
-            mrow[w * nthr] = bits;
+            mrow[w * MS] = bits;
             cnt += __popc(bits);
         }
     } else {
@@ -504,7 +620,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
             } else {
                 for (int kk = 0; kk < kend; ++kk) body(kk);
             }
-            mrow[w * nthr] = bits;
+            mrow[w * MS] = bits;
             cnt += __popc(bits);
         }
     }
@@ -566,31 +682,49 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
             int kd = -1;
             if constexpr (PA32) { if (valid && ((i >> 1) % LANES) == sub) kd = 2 * ((i >> 1) / LANES) + (i & 1); }
             else { if (valid && (i % LANES) == sub) kd = i / LANES; }
-            if (kd >= 0) { mrow[(kd >> 5) * nthr] &= ~(1u << (kd & 31)); --cnt; }
+            if (kd >= 0) { mrow[(kd >> 5) * MS] &= ~(1u << (kd & 31)); --cnt; }
         }
-        int w = 0;
-        unsigned cand = nw > 0 ? mrow[0] : 0u, ex = 0;
-        const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe);   // 32-bit shared address: stays in a register
-        for (int c = 0; c < cnt; ++c) {                     // counted loop: cnt candidates are known to exist
-            while (cand == 0) {                             // word exhausted: publish its exact bits, fetch the next
-                mrow[w * nthr] = ex; deg += __popc(ex); ex = 0;
-                ++w;
-                cand = mrow[w * nthr];
-            }
-            const unsigned low = cand & (0u - cand);        // lowest candidate bit
+        // One flat loop per lane over its candidates, ascending j.  Advancing to the next mask word is predicated
+        // straight-line code (some lane of the warp advances in almost every iteration) with the following word
+        // prefetched; a candidate that turns out not to be a neighbour has its bit cleared in place (shared-memory
+        // RED), so after the loop the words hold the exact adjacency bits.
+        const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe);   // 32-bit shared addresses: stay in registers
+        unsigned waddr = (unsigned)__cvta_generic_to_shared(mrow);       // current mask word of this thread
+        const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 32u : 0u);
+        unsigned cand = 0, nxt = 0;
+        if (nw > 0) { cand = mrow[0]; nxt = mrow[MS]; }     // (the mask region has one spare word row)
+        int jb = 0;                                         // bit position of the current word's bit 0
+        int left = cnt;                                     // candidates still to refine: they are known to exist
+        while (left > 0) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "setp.eq.u32 p, %0, 0;\n\t"
+                         "@p mov.u32 %0, %1;\n\t"
+                         "@p add.u32 %2, %2, %4;\n\t"
+                         "@p add.s32 %3, %3, 32;\n\t"
+                         "@p ld.shared.u32 %1, [%2+%4];\n\t}"
+                         : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(jb) : "n"(MS * 4) : "memory");
+            const unsigned low = cand & (0u - cand);        // lowest candidate bit (0: an empty word, the lane idles)
             cand ^= low;
-            const int k = 31 - __clz((int)low);
+            const int k = bfind(low);
             int j;
-            if constexpr (LANES == 1) j = w * 32 + k;       // one thread per row: bit position == agent index
-            else j = j_of(w * 32 + k);
-            const double4 xj = lds_state(xe_s + (unsigned)j * 32u);
-            bool adj;
-            if constexpr (EXACT) adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
-            else adj = refine_fast<PA32>(xi, xj, R2r, Rmr, A);
-            if (adj) ex |= low;
+            if constexpr (LANES == 1) j = jb + k;           // one thread per row: bit position == agent index
+            else j = j_of(jb + k);
+            // (an idle lane reads a harmless agent: not itself, so r2 > 0 and every masked term stays finite)
+            const unsigned xaddr = low ? xe_s + (unsigned)j * 32u : xdummy;
+            if constexpr (EXACT) {
+                if (low != 0) {
+                    const double4 xj = lds_state(xaddr);
+                    const bool adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
+                    deg += adj ? 1 : 0;
+                    if (!adj) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(waddr), "r"(~low) : "memory");
+                    --left;
+                }
+            } else {
+                refine_fast_pred<PA32>(xi, xaddr, low, waddr, R2r, Rmr, A, deg, left);
+            }
         }
-        if (nw > 0) { mrow[w * nthr] = ex; deg += __popc(ex); }    // words after w held no candidates: already zero
     }
+    __syncwarp();                                           // reconverge here: the epilogue runs with all 32 lanes
 
     // ---- reduce across the LANES threads of a row ----------------------------------------------------------
     if constexpr (LANES > 1) {
@@ -611,7 +745,14 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     if (valid && sub == 0) {
         if (a.values) {
             TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
-            v[0] = (TO)A.f0; v[1] = (TO)A.f1; v[2] = (TO)A.f2; v[3] = (TO)A.f3; v[4] = (TO)A.f4; v[5] = (TO)A.f5;
+            if constexpr (PA32) {                       // 24 B per row, 8-byte aligned: three float2 stores
+                float2 *v2 = reinterpret_cast<float2 *>(v);
+                v2[0] = make_float2((float)A.f0, (float)A.f1); v2[1] = make_float2((float)A.f2, (float)A.f3);
+                v2[2] = make_float2((float)A.f4, (float)A.f5);
+            } else {
+                double2 *v2 = reinterpret_cast<double2 *>(v);   // 48 B per row, 16-byte aligned
+                v2[0] = make_double2(A.f0, A.f1); v2[1] = make_double2(A.f2, A.f3); v2[2] = make_double2(A.f4, A.f5);
+            }
         }
         if (a.u_next) {
             double ux, uy;
@@ -630,12 +771,16 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
                     sdx = fma((double)N, xi.z - rx, -(st[0] - (double)N * rx));
                     sdy = fma((double)N, xi.w - ry, -(st[1] - (double)N * ry));
                 }
-                const double ia = a.inv_ascale;                  // one extra rounding vs a true divide
-                ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * ia;
-                uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * ia;
+                // clip(v, +-10) / ascale, then the variant's clip (flocking_stoch.py:43), as ONE clamp of v * (1/ascale)
+                // to +-ulim = min(10 / ascale, u_clip) (host): same values, saturated or not; one rounding vs a true divide
+                const double ia = a.inv_ascale, ul = a.ulim;
+                ux = fmin(fmax((-2.0 * A.gx - sdx) * ia, -ul), ul);
+                uy = fmin(fmax((-sdy - 2.0 * A.gy) * ia, -ul), ul);
             }
-            if (a.var.u_clip > 0.0) {                    // FlockingStochastic.controller (flocking_stoch.py:43)
-                ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
+            if constexpr (EXACT) {
+                if (a.var.u_clip > 0.0) {                // FlockingStochastic.controller (flocking_stoch.py:43)
+                    ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
+                }
             }
             reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
         }
@@ -643,24 +788,8 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
 
     // ---- dense adj_mean rows ---------------------------------------------------------------------------------------
     if (net == nullptr) return;
-    if (a.out_mode == 1) {
-        // small rows: expand the warp's 32 rows from their exact bit masks (LANES == 1, full rows; host guarantees it)
-        if constexpr (LANES == 1) {
-            TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
-            idg_s[tid] = idg;
-            __syncwarp();                                    // the lanes' mask words and 1/deg (shared memory) are complete
-            const int wr0 = r0 + (tid - lane);               // first flat row of this warp == its global row (nre == N)
-            const int nrows = min(32, r1 - wr0);
-            if (nrows > 0 && !(a.tune & 2)) {
-                TO *wout = net + (size_t)wr0 * N;
-                const unsigned *wm = masks + (tid - lane);
-                const TO *idgs = idg_s + (tid - lane);
-                constexpr int VMAX = 16 / (int)sizeof(TO);
-                if (N % VMAX == 0) expand_rows<TO, VMAX>(wout, wm, nthr, idgs, N, nrows, lane);
-                else if (VMAX == 4 && N % 2 == 0) expand_rows<TO, 2>(wout, wm, nthr, idgs, N, nrows, lane);
-                else expand_rows<TO, 1>(wout, wm, nthr, idgs, N, nrows, lane);
-            }
-        }
+    if (a.out_mode == 1) {       // small full rows (LANES == 1; host guarantees it): expand_window() does the rest
+        if constexpr (LANES == 1) idg_s[tid] = idg;
         return;
     }
     // large rows: scatter the few non-zero entries (1/deg) into the warp's zero-filled rows.  Every lane that queued
@@ -673,13 +802,53 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
         int w = 0;
         unsigned ex = nw > 0 ? mrow[0] : 0u;
         while (w < nw) {
-            if (ex == 0) { ++w; ex = (w < nw) ? mrow[w * nthr] : 0u; }
+            if (ex == 0) { ++w; ex = (w < nw) ? mrow[w * MS] : 0u; }
             if (ex != 0) {
                 const int k = __ffs(ex) - 1;
                 ex &= ex - 1;
                 orow[j_of(w * 32 + k)] = idg;
             }
         }
+    }
+}
+
+
+// ---- small rows: every warp expands its own 32 rows of the window [r0, r1) from their exact bit masks (LANES == 1) -----
+template <typename TO>
+__device__ __forceinline__ void expand_window(TO *network, const int N, const int tune, const unsigned *masks, const TO *idg_s,
+                                              const int r0, const int r1) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    __syncwarp();                                    // the lanes' mask words and 1/deg (shared memory) are complete
+    const int wr0 = r0 + (tid - lane);               // first flat row of this warp == its global row (nre == N)
+    const int nrows = min(32, r1 - wr0);
+    if (nrows > 0 && !(tune & 2)) {
+        TO *wout = network + (size_t)wr0 * N;
+        const unsigned *wm = masks + (tid - lane);
+        const TO *idgs = idg_s + (tid - lane);
+        constexpr int VMAX = 16 / (int)sizeof(TO);
+        if (N % VMAX == 0) expand_rows<TO, VMAX>(wout, wm, idgs, N, nrows, lane);
+        else if (VMAX == 4 && N % 2 == 0) expand_rows<TO, 2>(wout, wm, idgs, N, nrows, lane);
+        else expand_rows<TO, 1>(wout, wm, idgs, N, nrows, lane);
+    }
+}
+
+// Resident-CTA targets: the fast kernels are latency bound (divergent refine loops), so occupancy matters more than
+// registers: 256-thread bound, FLOCK_MINB CTAs per SM.  EXACT keeps its registers.
+// One CTA = one window.
+template <typename TO, int LANES, bool EXACT, bool KNN>
+__global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
+    static_assert(!EXACT || (!std::is_same<TO, float>::value && LANES == 1), "EXACT is fp64, one thread per row");
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);
+    TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
+    const Win win = window_of(a, blockIdx.x);
+    stage_window<TO, EXACT>(a, smem, win);
+    __syncthreads();
+    window_stats<TO, EXACT>(a, smem, win);
+    compute_rows<TO, LANES, EXACT, KNN>(a, smem, masks, idg_s, win);
+    if constexpr (LANES == 1) {
+        if (a.network != nullptr && a.out_mode == 1)
+            expand_window<TO>(reinterpret_cast<TO *>(a.network), a.N, a.tune, masks, idg_s, win.r0, win.r1);
     }
 }
 
