@@ -125,8 +125,10 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
     }
     k.tune = p->reserved >> 8;
-    // small full rows: expand in the warp (coalesced stores); large rows: bulk zero-fill + scatter
-    k.out_mode = (lanes == 1 && nrows == N && (size_t)N * tbytes <= 2048 && !((p->reserved >> 8) & 16)) ? 1 : 0;
+    // full rows, one thread per row: expand in the warp (coalesced stores, every byte written once);
+    // sharded rows / several lanes per row: bulk zero-fill + scatter
+    // (exact-order mode with long rows keeps the bulk fill: its long sequential compute phase hides the background fill)
+    k.out_mode = (lanes == 1 && nrows == N && !(pl.exact && (size_t)N * tbytes > 2048) && !((p->reserved >> 8) & 16)) ? 1 : 0;
     k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
     k.ulim = 10.0 * k.inv_ascale;
     if (p->u_clip > 0.0) k.ulim = std::min(k.ulim, p->u_clip);

@@ -309,11 +309,19 @@ __device__ __forceinline__ void expand_rows(TO *wout, const unsigned *wm, const 
             dst += dstep;
         }
     } else {
+        // long rows (more than 32 groups): the lane's groups are cv = lane + 32 t, so its bit offset within a mask word is
+        // a constant and its word advances by V per step: per group one LDS, the selects and one coalesced 16-byte store
+        // (a warp-wide store covers 512 contiguous bytes of the row).  Every byte of the row is written exactly once.
+        const int sh = (lane * V) & 31;
+        const unsigned *mp0 = wm + ((lane * V) >> 5) * MS;
         for (int r = 0; r < nrows; ++r) {
             const TO v = idgs[r];
+            const unsigned *mp = mp0 + r;
+            TO *dst = wout + (size_t)r * N + lane * V;
+#pragma unroll 4
             for (int cv = lane; cv < nv; cv += 32) {
-                const int c = cv * V;
-                store_group<TO, V>(wout + (size_t)r * N + c, wm[(c >> 5) * MS + r] >> (c & 31), v, true);
+                store_group<TO, V>(dst, *mp >> sh, v, true);
+                mp += V * MS; dst += 32 * V;
             }
         }
     }
