@@ -276,7 +276,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     K, W = max(1, args.steps), max(3, args.warmup)
     x0 = initial_states_fast(E, N, seed=1234 + rank * E)
     env = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=local_rank,
-                      adjacency_mode=args.adjacency)
+                      adjacency_mode=args.adjacency, lanes=args.env_lanes)
     env.reset(x0)
     rewards = torch.zeros(K, E, dtype=env.dtype, device=env.device)
     env.rollout(W)
@@ -369,6 +369,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gather", type=int, default=0, help="C5 diagnostic: skip the all-gather (results wrong; timing only)")
     ap.add_argument("--lanes", type=int, default=16, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
+    ap.add_argument("--env-lanes", type=int, default=0, help="env batches: threads per row (0 = library heuristic)")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()
