@@ -112,8 +112,7 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     k.off_masks = align16(k.off_pf + size_pf);
     const size_t size_lists = (size_t)flock::MS * (W + 1) * 4;     // word-major, fixed stride, one spare word row (prefetch)
     k.off_stats = align16(k.off_masks + size_lists);
-    k.off_zero = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);
-    k.off_idg = align16((size_t)k.off_zero + flock::ZERO_BYTES);      // 1/deg per row (in-warp row expansion)
+    k.off_idg = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);      // 1/deg per row (in-warp row expansion)
     pl.smem = (size_t)k.off_idg + (size_t)threads * 8;
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",

@@ -62,23 +62,12 @@ struct KArgs {
     StepVariant var;     // flocking variants (leader / stochastic); defaults reproduce FlockingRelative
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
-    unsigned off_xs, off_pf, off_masks, off_stats, off_zero, off_idg;
-    int out_mode; // dense adjacency output: 0 = bulk zero-fill + scatter of the non-zeros; 1 = in-warp row expansion
+    unsigned off_xs, off_pf, off_masks, off_stats, off_idg;
+    int out_mode; // dense adjacency output: 0 = zero-fill up front + the non-zeros stored over it; 1 = in-warp row expansion
     int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
 };
 
 constexpr int MS = FLOCK_MAXT;     // mask words are stored word-major with a fixed stride: word w of thread t at masks[w * MS + t]
-constexpr int ZERO_BYTES = 2048;   // shared zero block: source of the bulk (TMA) zero-fill of the dense adjacency
-
-// ---- bulk async copy (TMA, 1-D) shared -> global ------------------------------------------------------------
-__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, unsigned bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // one agent's state from shared memory by 32-bit shared address (two LDS.128, no generic-address arithmetic)
 __device__ __forceinline__ double4 lds_state(const unsigned saddr) {
@@ -366,15 +355,8 @@ template <typename TO, bool EXACT>
 __device__ __forceinline__ void stage_window(const KArgs &a, unsigned char *smem, const Win win) {
     FLOCK_WIN_LOCALS
 
-    // ---- zero block for the bulk fill, stats flags ------------------------------------------------------------
-    {
-        if (a.out_mode == 0) {
-            float4 *zb = reinterpret_cast<float4 *>(smem + a.off_zero);
-            for (int q = tid; q < ZERO_BYTES / 16; q += nthr) zb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if constexpr (!EXACT) for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
-        fence_async_smem();      // generic-proxy zeros -> visible to the async proxy (TMA) after the barrier
-    }
+    // ---- stats flags ----------------------------------------------------------------------------------------------------
+    if constexpr (!EXACT) for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
 
     // ---- prologue: load, integrate, publish x', stage (one flat loop over the agents of the staged envs) -----------
     {
@@ -496,10 +478,11 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
     unsigned *mrow = masks + tid;                           // word-major: word w of this thread at mrow[w * MS]
     const size_t grow = (size_t)env * N + i;                // global row (agent) index
 
-    // ---- per-warp bulk zero-fill of the warp's rows of the dense adjacency ---------------------------------------
-    // The rows of a warp are consecutive flat rows; with full rows (nre == N) they are ONE contiguous run in
-    // memory, otherwise one run per env they belong to.  Lane l queues the l-th 2 KB piece of the run.
-    bool bulk_pending = false;
+    // ---- out_mode 0: zero-fill of the warp's rows of the dense adjacency, up front -------------------------------------
+    // The rows of a warp are consecutive flat rows; with full rows (nre == N) they are ONE contiguous run in memory,
+    // otherwise one run per env they belong to.  Plain coalesced 16-byte streaming stores (a warp store covers 512
+    // contiguous bytes); they drain to HBM while the warp computes, and the few non-zero entries are stored over them at
+    // the end.  (1-D TMA bulk stores from a shared zero block throttle at ~3.6 TB/s; direct stores reach 6.3.)
     if (net && a.out_mode == 0 && !(a.tune & 1)) {
         const int wr0 = r0 + (tid - lane) / LANES;                           // first flat row of this warp
         const int wr1 = min(wr0 + 32 / LANES, r1);
@@ -515,15 +498,16 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
             TO *out = net + base;
             if ((unsigned)lane < headn) out[lane] = TO(0);
             if ((unsigned)lane < total - (headn + nvec * VEC)) out[headn + nvec * VEC + lane] = TO(0);
-            char *dst = reinterpret_cast<char *>(out + headn);
-            const unsigned bytes = nvec * 16u;
-            for (unsigned off = (unsigned)lane * ZERO_BYTES; off < bytes; off += 32u * ZERO_BYTES) {
-                bulk_store_s2g(dst + off, smem + a.off_zero, min((unsigned)ZERO_BYTES, bytes - off));
-                bulk_pending = true;
+            float4 *d4 = reinterpret_cast<float4 *>(out + headn);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned v = (unsigned)lane;
+            for (; v + 7u * 32u < nvec; v += 8u * 32u) {
+#pragma unroll
+                for (unsigned q = 0; q < 8u; ++q) __stcs(d4 + v + q * 32u, z4);
             }
+            for (; v < nvec; v += 32u) __stcs(d4 + v, z4);
             s0 = s1;
         }
-        if (bulk_pending) bulk_commit();
     }
 
     Acc A;
@@ -800,10 +784,8 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
         if constexpr (LANES == 1) idg_s[tid] = idg;
         return;
     }
-    // large rows: scatter the few non-zero entries (1/deg) into the warp's zero-filled rows.  Every lane that queued
-    // bulk zero stores waits for them and orders them (async proxy) before the generic-proxy stores below;
-    // __syncwarp then releases the warp.  A warp only ever touches its own rows.
-    if (bulk_pending && !(a.tune & 32)) { bulk_wait_all(); fence_async_all(); }
+    // out_mode 0: store the few non-zero entries (1/deg) over the warp's zero-filled rows.  A warp only ever touches its
+    // own rows; __syncwarp orders the lanes' zero stores before the non-zero stores.
     __syncwarp();
     if (valid && !(a.tune & 2)) {
         TO *orow = net + grow * N;

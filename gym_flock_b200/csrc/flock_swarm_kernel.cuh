@@ -71,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, unsigned bytes, void *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
