@@ -66,7 +66,7 @@ def _cpu_worker(args):
     return x.shape[0]
 
 
-def cpu_numpy_port(cfg, envs_per_core=8, steps=20, procs=None):
+def cpu_numpy_port(cfg, envs_per_core=8, steps=20, procs=None, pairs_per_core=None):
     """The reference's algorithm (NumPy restatement, dense [N,N,*] temporaries) on all host cores: independent
     env slices, one process per core.  Returns (pairs/s, seconds, sample description, cores)."""
     import multiprocessing as mp
@@ -74,6 +74,9 @@ def cpu_numpy_port(cfg, envs_per_core=8, steps=20, procs=None):
     cores = procs or os.cpu_count() or 1
     N = cfg["N"]
     per = max(1, min(envs_per_core, max(1, int(2.0e6 / (N * N)))))     # keep a sample a few seconds per core
+    if pairs_per_core:                                                  # bound the work per core (pairs, all steps)
+        per = max(1, min(envs_per_core, int(pairs_per_core / (N * N * steps)) or 1))
+        steps = max(1, min(steps, int(pairs_per_core / (N * N * per)) or 1))
     E = per * cores
     x = initial_states_fast(E, N, seed=1234)
     knn = cfg["env_id"] == "Flocking-v0"
@@ -94,7 +97,7 @@ def cpu_c_port(cfg, steps=20):
     from oracle import c_oracle
     N = cfg["N"]
     threads = c_oracle.threads()
-    E = max(threads, min(4096, int(threads * 4.0e7 / (N * N * steps)) or 1))
+    E = max(threads, min(4096, int(threads * 4.0e8 / (N * N * steps)) or 1))
     x = initial_states_fast(E, N, seed=1234)
     c_oracle.rollout(x[:threads], 1, want_network=False)
     t0 = time.perf_counter()
@@ -250,8 +253,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         return run_swarm(args, cfg, rank, world, local_rank)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:       # before CUDA init (fork-safe)
-        r, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=8, steps=20)
-        rc, dtc, samplec, thr = cpu_c_port(cfg)
+        # a bounded sample of the same workload, ~10 s of CPU work for the NumPy port (about 1e8 pair-interactions/s
+        # on 16 cores at N=100), a few seconds for the C/OpenMP restatement
+        r, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=32, steps=200, pairs_per_core=6.5e7)
+        rc, dtc, samplec, thr = cpu_c_port(cfg, steps=100)
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt,
                "c_port": {"value": rc, "unit": UNIT, "cores": thr, "sample": samplec, "seconds": dtc,
                           "what": "oracle/flock_oracle.c, OpenMP over envs"}}

@@ -6,11 +6,11 @@
 
 The numerics live in libflock_b200.so (hand-written sm_100a CUDA behind the C ABI of include/flock_b200.h).
 """
-from .envs import (FlockingEnv, FlockingLeaderEnv, FlockingRelativeEnv, FlockingStochasticEnv,  # noqa: F401
+from .envs import (FlockingEnv, FlockingLeaderEnv, FlockingObstacleEnv, FlockingRelativeEnv, FlockingStochasticEnv,  # noqa: F401
                    FlockingTwoFlocksEnv, TimeLimit, make, register_with_gym)
 from .host_env import HostFlockBatch  # noqa: F401
 
-__all__ = ["FlockingEnv", "FlockingRelativeEnv", "FlockingTwoFlocksEnv", "FlockingLeaderEnv", "FlockingStochasticEnv", "TimeLimit", "make", "register_with_gym", "HostFlockBatch",
+__all__ = ["FlockingEnv", "FlockingRelativeEnv", "FlockingTwoFlocksEnv", "FlockingLeaderEnv", "FlockingStochasticEnv", "FlockingObstacleEnv", "TimeLimit", "make", "register_with_gym", "HostFlockBatch",
            "FlockVecEnv", "SwarmEnv"]
 
 

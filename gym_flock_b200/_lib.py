@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 FLOCK_CENTRALIZED = 0x1
 FLOCK_EXACT_ORDER = 0x2
 FLOCK_KNN_OBS = 0x4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FlockParams(ctypes.Structure):
@@ -36,7 +36,7 @@ class FlockParams(ctypes.Structure):
                 ("row_lo", ctypes.c_int32), ("row_hi", ctypes.c_int32),
                 ("lanes", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("step_scale", ctypes.c_double), ("state_scale", ctypes.c_double), ("u_clip", ctypes.c_double),
-                ("n_leaders", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+                ("n_leaders", ctypes.c_int32), ("n_obstacles", ctypes.c_int32)]
 
 
 class FlockError(RuntimeError):
@@ -129,7 +129,7 @@ def make_params(n_envs: int, n_agents: int, comm_radius: float = 0.9, dt: float 
                 action_scalar: float = 10.0, centralized: bool = True, exact: bool = False,
                 knn_obs: bool = False, knn: int = 7, rows: tuple | None = None, lanes: int = 0,
                 comm_radius2: float | None = None, step_scale: float = 0.0, state_scale: float = 0.0,
-                u_clip: float = 0.0, n_leaders: int = 0) -> FlockParams:
+                u_clip: float = 0.0, n_leaders: int = 0, n_obstacles: int = 0) -> FlockParams:
     flags = (FLOCK_CENTRALIZED if centralized else 0) | (FLOCK_EXACT_ORDER if exact else 0) | \
             (FLOCK_KNN_OBS if knn_obs else 0)
     r2 = comm_radius * comm_radius if comm_radius2 is None else comm_radius2   # flocking_relative.py:44
@@ -137,7 +137,7 @@ def make_params(n_envs: int, n_agents: int, comm_radius: float = 0.9, dt: float 
     return FlockParams(int(n_envs), int(n_agents), float(comm_radius), float(r2), float(dt),
                        float(action_scalar), flags, int(knn), int(lo), int(hi), int(lanes),
                        int(os.environ.get("FLOCK_TUNE", "0")), float(step_scale), float(state_scale), float(u_clip),
-                       int(n_leaders), 0)
+                       int(n_leaders), int(n_obstacles))
 
 
 def require_device() -> int:

@@ -24,6 +24,7 @@ flock::StepVariant step_variant(const FlockParams *p) {
     v.state_scale = (p->state_scale != 0.0) ? p->state_scale : 1.0;
     v.u_clip = p->u_clip;
     v.n_leaders = p->n_leaders;
+    v.n_obstacles = p->n_obstacles;
     return v;
 }
 
@@ -61,8 +62,9 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     if (!p) return fail(FLOCK_EINVAL, "params is NULL");
     const int E = p->n_envs, N = p->n_agents;
     if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
-    if (p->n_leaders < 0 || p->n_leaders > N || p->u_clip < 0.0 || p->state_scale < 0.0)
-        return fail(FLOCK_EINVAL, "bad variant parameters (n_leaders=%d u_clip=%g state_scale=%g)", p->n_leaders, p->u_clip, p->state_scale);
+    if (p->n_leaders < 0 || p->n_leaders > N || p->n_obstacles < 0 || p->n_obstacles > N || p->u_clip < 0.0 || p->state_scale < 0.0)
+        return fail(FLOCK_EINVAL, "bad variant parameters (n_leaders=%d n_obstacles=%d u_clip=%g state_scale=%g)", p->n_leaders,
+                    p->n_obstacles, p->u_clip, p->state_scale);
     if ((long long)E * N > (1LL << 30)) return fail(FLOCK_EUNSUPPORTED, "E*N too large");
     int row_lo = p->row_lo, row_hi = p->row_hi;
     if (row_lo == 0 && row_hi == 0) row_hi = N;
@@ -264,6 +266,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     if (p->flags & FLOCK_EXACT_ORDER)
         return fail(FLOCK_EUNSUPPORTED, "FLOCK_EXACT_ORDER is offered by the env-resident path only (flock_step_f64)");
     if ((p->flags & FLOCK_KNN_OBS) && p->knn != flock::KNN_K) return fail(FLOCK_EUNSUPPORTED, "knn=%d", p->knn);
+    if (p->n_obstacles != 0) return fail(FLOCK_EUNSUPPORTED, "n_obstacles is offered by the env-resident path only (flock_step_*)");
     int row_lo = p->row_lo, row_hi = p->row_hi;
     if (row_lo == 0 && row_hi == 0) row_hi = N;
     if (row_lo < 0 || row_hi > N || row_lo >= row_hi) return fail(FLOCK_EINVAL, "bad row range [%d,%d)", row_lo, row_hi);

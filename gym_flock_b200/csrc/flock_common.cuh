@@ -83,10 +83,12 @@ __device__ __forceinline__ double4 integrate_exact(double4 x, double2 u, double 
 //   FlockingRelative/Flocking : a = u*10                                    flocking_relative.py:96-105
 //   FlockingLeader            : a = u, leaders (j < n_leaders) get a*0       flocking_leader.py:21-31
 //   FlockingStochastic        : u = clip(u, +-c); a = u*6; x = x*6; step; x = x/6      flocking_stoch.py:14-33
-struct StepVariant { double step_scale, state_scale, u_clip; int n_leaders; };
+//   FlockingObstacle          : a = u, obstacles (j < n_obstacles) are not actuated; velocity differences with an
+//                               obstacle row or column are zero                flocking_obstacle.py:33-50,78-82
+struct StepVariant { double step_scale, state_scale, u_clip; int n_leaders, n_obstacles; };
 __device__ __forceinline__ double4 integrate_variant(double4 x, double2 u, const int j, const double dt, const StepVariant v) {
     if (v.u_clip > 0.0) { u.x = fmin(fmax(u.x, -v.u_clip), v.u_clip); u.y = fmin(fmax(u.y, -v.u_clip), v.u_clip); }
-    if (j < v.n_leaders) { u.x = 0.0; u.y = 0.0; }          // (u*dt*dt*0.5)*0 = 0: the position/velocity keep their drift only
+    if (j < v.n_leaders || j < v.n_obstacles) { u.x = 0.0; u.y = 0.0; }          // (u*dt*dt*0.5)*0 = 0: the position/velocity keep their drift only
     const bool scaled = (v.state_scale != 1.0);
     if (scaled) {
         x.x = __dmul_rn(x.x, v.state_scale); x.y = __dmul_rn(x.y, v.state_scale);

@@ -123,10 +123,11 @@ struct Acc {
 };
 
 // EXACT refine of one candidate pair: Appendix B of SURVEY.md, one rounding per operation, NumPy's order.
+// novel: the pair involves an obstacle (FlockingObstacle), its velocity difference is zero (flocking_obstacle.py:81-82)
 __device__ __forceinline__ bool refine_exact(const double4 xi, const double4 xj, const double R, const double R2,
-                                             const bool cen, Acc &A) {
+                                             const bool cen, Acc &A, const bool novel = false) {
     const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
-    const double dvx = __dsub_rn(xi.z, xj.z), dvy = __dsub_rn(xi.w, xj.w);
+    const double dvx = novel ? 0.0 : __dsub_rn(xi.z, xj.z), dvy = novel ? 0.0 : __dsub_rn(xi.w, xj.w);
     const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     const bool a = r2 < R2;
     const double r4 = __dmul_rn(r2, r2);
@@ -363,7 +364,7 @@ __device__ __forceinline__ void stage_window(const KArgs &a, unsigned char *smem
         const int nag = nenv * N;
         const size_t a0 = (size_t)e0 * N;
         // the plain step (FlockingRelative / Flocking) keeps the loop body short; the variants take the general path
-        const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
+        const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.n_obstacles == 0) && (a.var.state_scale == 1.0);
         struct Ag { double4 x; double2 u, ref; int ge, j; };
         // all loads first (state, action, the env's origin) ...
         auto fetch = [&](const int idx, Ag &g) {
@@ -473,6 +474,7 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
     const int env = e0 + g;
     const int i = valid ? a.row_lo + (fr - env * nre) : 0;
     const bool cen = a.centralized != 0;
+    const int nobs = a.var.n_obstacles;                     // FlockingObstacle: agents [0, nobs)
     const double4 *xe = xs + g * N;
     const double4 xi = xe[i];
     unsigned *mrow = masks + tid;                           // word-major: word w of this thread at mrow[w * MS]
@@ -594,8 +596,8 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                     const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
                     r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     c = (r2 < a.R2) || !(r2 > a.R);
-                    if (cen) {       // sum_j (v_i - v_j) over ALL j, sequential (flocking_relative.py:204-208)
-                        A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));
+                    if (cen && !(i < nobs || j < nobs)) {   // sum_j (v_i - v_j) over ALL j, sequential (flocking_relative.py:204-208);
+                        A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));   // obstacle rows / columns contribute exact zeros
                         A.s1 = __dadd_rn(A.s1, __dsub_rn(xi.w, xj.w));
                     }
                 } else {
@@ -706,7 +708,7 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
             if constexpr (EXACT) {
                 if (low != 0) {
                     const double4 xj = lds_state(xaddr);
-                    const bool adj = refine_exact(xi, xj, a.R, a.R2, cen, A);
+                    const bool adj = refine_exact(xi, xj, a.R, a.R2, cen, A, i < nobs || j < nobs);
                     deg += adj ? 1 : 0;
                     if (!adj) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(waddr), "r"(~low) : "memory");
                     --left;
@@ -726,6 +728,23 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
             A.f3 += shfl_xor(A.f3, m); A.f4 += shfl_xor(A.f4, m); A.f5 += shfl_xor(A.f5, m);
             A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
             deg += shfl_xor(deg, m);
+        }
+    }
+
+    // ---- FlockingObstacle, fast modes: velocity differences with an obstacle row or column are zero --------------------
+    // (flocking_obstacle.py:81-82).  The refine loop summed them like any other pair; take the (at most nobs) terms out
+    // again with the same adjacency test.  EXACT handled them in place.
+    double osx = 0.0, osy = 0.0;                            // sum over the obstacles of (v_j - v_0)   (centralized alignment)
+    if constexpr (!EXACT) {
+        if (nobs > 0 && valid && sub == 0) {
+            if (i < nobs) { A.f0 = 0.0; A.f3 = 0.0; }
+            for (int j = 0; j < nobs; ++j) {
+                const double4 xj = xe[j];
+                osx += xj.z - xe[0].z; osy += xj.w - xe[0].w;
+                if (j == i || i < nobs) continue;
+                const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                if (fma(dx, dx, dy * dy) < R2r) { A.f0 -= xi.z - xj.z; A.f3 -= xi.w - xj.w; }
+            }
         }
     }
 
@@ -762,6 +781,10 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                     const double rx = xe[0].z, ry = xe[0].w;
                     sdx = fma((double)N, xi.z - rx, -(st[0] - (double)N * rx));
                     sdy = fma((double)N, xi.w - ry, -(st[1] - (double)N * ry));
+                    if (nobs > 0) {                          // only the N - nobs ordinary agents count, and only for them
+                        sdx = (i < nobs) ? 0.0 : fma((double)(N - nobs), xi.z - rx, -((st[0] - (double)N * rx) - osx));
+                        sdy = (i < nobs) ? 0.0 : fma((double)(N - nobs), xi.w - ry, -((st[1] - (double)N * ry) - osy));
+                    }
                 }
                 // clip(v, +-10) / ascale, then the variant's clip (flocking_stoch.py:43), as ONE clamp of v * (1/ascale)
                 // to +-ulim = min(10 / ascale, u_clip) (host): same values, saturated or not; one rounding vs a true divide

@@ -122,7 +122,7 @@ class FlockingRelativeEnv:
         return False
 
     def _variant(self) -> dict:
-        """Step-variant parameters of the C ABI (FlockParams.step_scale / state_scale / u_clip / n_leaders)."""
+        """Step-variant parameters of the C ABI (FlockParams.step_scale / state_scale / u_clip / n_leaders / n_obstacles)."""
         return {}
 
     def _engine(self) -> HostFlockBatch:
@@ -406,6 +406,65 @@ class FlockingLeaderEnv(FlockingRelativeEnv):
         return out
 
 
+class FlockingObstacleEnv(FlockingRelativeEnv):
+    """gym-flock's 'FlockingObstacle-v0' (flocking_obstacle.py:14-104): the first n_obstacles agents are static
+    obstacles -- not actuated (:40-46), and every velocity difference with an obstacle row or column is zero (:81-82);
+    the action is applied unscaled (:37).  Same kernel with FlockParams.n_obstacles / step_scale = 1."""
+
+    def __init__(self, precision: str = "fp64-exact", device: int = 0):
+        super().__init__(precision=precision, device=device)
+        self.n_obstacles = 4                                         # :19
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:self.n_obstacles] = 0
+        self.r_max = 3.0                                             # :23
+        self.line1 = None
+        self.line2 = None
+
+    def params_from_cfg(self, args):
+        super().params_from_cfg(args)
+        self.mask = np.ones((self.n_agents,))
+        self.mask[0:self.n_obstacles] = 0
+
+    def _variant(self) -> dict:
+        return dict(step_scale=1.0, n_obstacles=int(self.n_obstacles))
+
+    def _engine(self):
+        # the engine is rebuilt when the number of obstacles changes (it is a launch parameter)
+        if self._eng is not None and getattr(self, "_eng_nobs", None) != int(self.n_obstacles):
+            self._eng.close()
+            self._eng = None
+        self._eng_nobs = int(self.n_obstacles)
+        return super()._engine()
+
+    def step(self, u):
+        """flocking_obstacle.py:33-50."""
+        assert u.shape == (self.n_agents, self.nu)
+        self._sync_device()
+        eng = self._engine()
+        self.u = u
+        eng.step(np.asarray(u, dtype=np.float64)[None])
+        self._x = eng.x[0].copy()
+        self._shadow = self._x.copy()
+        self._pull(eng)
+        return (self.state_values, self.state_network), self.instant_cost(), False, {}
+
+    def reset(self):
+        """flocking_obstacle.py:57-72: deterministic lattice moving down at 7 m/s towards a 2x2 block of obstacles."""
+        n, no = self.n_agents, self.n_obstacles
+        x = np.zeros((n, self.nx_system))
+        x[:, 0:2] = _grid(n)
+        x[:, 2:4] = [0, -7.0]
+        x[0:no, 0:2] = _grid(no, side=2) * 0.5
+        x[0:no, 1] -= 10.0
+        x[0:no, 2:4] = 0
+        self.mean_vel = np.mean(x[no:, 2:4], axis=0)
+        self._x = x
+        self._shadow = None
+        self.init_vel = self._x[no:, 2:4]
+        self.compute_helpers()
+        return (self.state_values, self.state_network)
+
+
 class FlockingStochasticEnv(FlockingRelativeEnv):
     """gym-flock's 'FlockingStochastic-v0' (flocking_stoch.py:5-45): actions clipped to +-0.5 and scaled by 6, the state is
     scaled by 6 around the Euler step, dt ~ N(0.12, 0.018) drawn per step from the global np.random stream."""
@@ -473,6 +532,7 @@ REGISTRY = {   # gym_flock/__init__.py:53-63, 90-94
     'FlockingTwoFlocks-v0': (FlockingTwoFlocksEnv, 500),   # SURVEY.md 8f "next #1": same kernel, different reset
     'FlockingLeader-v0': (FlockingLeaderEnv, 200),         # gym_flock/__init__.py:65-69
     'FlockingStochastic-v0': (FlockingStochasticEnv, 500), # gym_flock/__init__.py:84-88
+    'FlockingObstacle-v0': (FlockingObstacleEnv, 200),     # gym_flock/__init__.py:72-76
 }
 
 

@@ -47,7 +47,8 @@ class HostFlockBatch:
     def __init__(self, n_envs: int, n_agents: int, comm_radius: float = 0.9, dt: float = 0.01,
                  centralized: bool = True, knn_obs: bool = False, precision: str = "fp64-exact",
                  device: int = 0, lanes: int = 0, comm_radius2: float | None = None, pinned: bool = True,
-                 step_scale: float = 0.0, state_scale: float = 0.0, u_clip: float = 0.0, n_leaders: int = 0):
+                 step_scale: float = 0.0, state_scale: float = 0.0, u_clip: float = 0.0, n_leaders: int = 0,
+                 n_obstacles: int = 0):
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         _lib.require_device()
@@ -58,7 +59,7 @@ class HostFlockBatch:
         self.knn_obs = bool(knn_obs)
         self._kw = dict(comm_radius=comm_radius, dt=dt, centralized=centralized, exact=self.exact,
                         knn_obs=knn_obs, lanes=lanes, comm_radius2=comm_radius2, step_scale=step_scale,
-                        state_scale=state_scale, u_clip=u_clip, n_leaders=n_leaders)
+                        state_scale=state_scale, u_clip=u_clip, n_leaders=n_leaders, n_obstacles=n_obstacles)
         self._params = _lib.make_params(self.E, self.N, **self._kw)
         ctx = ctypes.c_void_p()
         _lib.check(_lib.lib().flock_ctx_create(ctypes.byref(ctx), ctypes.byref(self._params),

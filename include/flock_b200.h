@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FLOCK_ABI_VERSION 2
+#define FLOCK_ABI_VERSION 3
 
 /* flags */
 #define FLOCK_CENTRALIZED   0x1   /* controller(centralized=True), flocking_relative.py:200-206 */
@@ -72,7 +72,8 @@ typedef struct FlockParams {
     double  u_clip;         /* FlockingStochastic: clip the action before the step and the controller output to
                              *   +-u_clip (flocking_stoch.py:16,43); 0 = none */
     int32_t n_leaders;      /* FlockingLeader: agents [0, n_leaders) are not actuated (flocking_leader.py:11-12,27-31) */
-    int32_t pad_;
+    int32_t n_obstacles;    /* FlockingObstacle: agents [0, n_obstacles) are not actuated and every velocity difference with
+                               one of them is zero (flocking_obstacle.py:19-20,33-50,81-82); env-resident path only */
 } FlockParams;
 
 int         flock_abi_version(void);

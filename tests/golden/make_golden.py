@@ -91,6 +91,8 @@ def run_variant(which, n, seed):
     """FlockingLeader-v0 / FlockingStochastic-v0 of the reference, state injected, 200-step expert rollout."""
     if which == "leader":
         env = ref_loader.load_variant("flocking_leader", "FlockingLeaderEnv")()
+    elif which == "obstacle":
+        env = ref_loader.load_variant("flocking_obstacle", "FlockingObstacleEnv")()
     else:
         env = ref_loader.load_variant("flocking_stoch", "FlockingStochasticEnv")()
     x0 = initial_state(n, seed=seed, min_dist=0.1)
@@ -98,6 +100,13 @@ def run_variant(which, n, seed):
     if which == "leader":
         env.mask = np.ones((n,)); env.mask[0:env.n_leaders] = 0
         x0[0:env.n_leaders, 2:4] = 1.75
+    if which == "obstacle":
+        env.mask = np.ones((n,)); env.mask[0:env.n_obstacles] = 0
+        if seed == 0:                      # the reference's own deterministic reset() (flocking_obstacle.py:57-72)
+            env.reset()
+            x0 = env.x.copy()
+        else:                              # injected state: obstacles at rest
+            x0[0:env.n_obstacles, 2:4] = 0
     env.x = x0.copy()
     env.compute_helpers()
     out = {"x0": x0.copy(), "values_0": env.state_values.copy(), "u_0": env.controller()}
@@ -117,7 +126,8 @@ def run_variant(which, n, seed):
 
 
 def main():
-    for which, n, seed in (("leader", 100, 31), ("stochastic", 100, 32), ("leader", 20, 33), ("stochastic", 33, 34)):
+    for which, n, seed in (("leader", 100, 31), ("stochastic", 100, 32), ("leader", 20, 33), ("stochastic", 33, 34),
+                           ("obstacle", 100, 0), ("obstacle", 40, 35)):
         np.savez_compressed(os.path.join(HERE, f"variant_{which}_n{n}.npz"), **run_variant(which, n, seed))
         print("wrote variant", which, n)
     for name, kind, n, cen, cr, dt, seed, md in CASES:

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(L):
             "flock_ctx_step", "flock_ctx_controller", "flock_last_error"} <= names
     for n in sorted(names):
         assert hasattr(L, n), n
-    assert L.flock_abi_version() == 2
+    assert L.flock_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_params_struct_layout_matches_header():

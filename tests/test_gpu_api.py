@@ -183,3 +183,59 @@ def test_leader_and_stochastic_variants_match_reference_golden(name, monkeypatch
     assert np.array_equal(rewards, g["rewards"])
     assert np.array_equal(net, g["adj_mean_200"])
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["variant_obstacle_n100", "variant_obstacle_n40"])
+def test_obstacle_variant_matches_reference_golden(name):
+    """FlockingObstacle-v0 through the same kernel (FlockParams.n_obstacles, step_scale = 1), bit-exact against the
+    reference's own rollouts: n100 starts from the reference's deterministic reset(), n40 from an injected state."""
+    import gym_flock_b200 as gf
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n = int(g["meta"][0])
+    env = gf.FlockingObstacleEnv()
+    if n == 100:
+        values0, net0 = env.reset()                                    # deterministic lattice (flocking_obstacle.py:57-72)
+        assert np.array_equal(env.x, g["x0"])
+    else:
+        env.n_agents = n
+        env.mask = np.ones((n,)); env.mask[0:env.n_obstacles] = 0
+        env.set_state(g["x0"])
+    assert np.array_equal(env.state_values, g["values_0"])
+    assert np.array_equal(env.controller(), g["u_0"])
+    rewards = np.zeros(200)
+    for t in range(1, 201):
+        u = env.controller()
+        (values, net), r, done, info = env.step(u)
+        rewards[t - 1] = r
+        if t in (1, 2, 50, 100, 200):
+            assert np.array_equal(env.x, g[f"x_{t}"]), t
+            assert np.array_equal(u, g[f"u_{t}"]), t
+            assert np.array_equal(values, g[f"values_{t}"]), t
+            assert np.array_equal((net > 0).astype(np.uint8), np.unpackbits(g[f"adj_{t}"], axis=1)[:, :n]), t
+    assert np.array_equal(rewards, g["rewards"])
+    assert np.array_equal(net, g["adj_mean_200"])
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-10), ("fp32", 1e-4)])
+@pytest.mark.parametrize("centralized", [True, False])
+def test_obstacle_variant_fast_modes(precision, tol, centralized):
+    """The fast modes take the obstacle terms out in the row epilogue: teacher-forced against the reference golden states
+    (features, adjacency, controller action) for both controller kinds."""
+    from gym_flock_b200 import HostFlockBatch
+    from oracle import flock_numpy as fnp
+    g = np.load(os.path.join(GOLDEN_DIR, "variant_obstacle_n100.npz"))
+    eng = HostFlockBatch(1, 100, centralized=centralized, precision=precision, step_scale=1.0, n_obstacles=4)
+    for key in ("x0", "x_1", "x_50", "x_100", "x_200"):
+        x = g[key]
+        eng.set_state(x[None])
+        h = fnp.compute_helpers_obstacle(x, 0.81, 4)
+        u_ref = fnp.controller(h, 0.9, centralized)
+        v = eng.values[0].astype(np.float64)
+        assert np.max(np.abs(v - h["values"])) <= tol * np.max(np.abs(h["values"])), key
+        assert np.array_equal(eng.network[0] > 0, h["adj"] > 0), key
+        u = eng.controller(centralized)[0]
+        assert np.max(np.abs(u - u_ref)) <= tol * max(np.max(np.abs(u_ref)), 1e-2), key
+    eng.close()

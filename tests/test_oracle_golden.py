@@ -70,6 +70,27 @@ import glob, os
 from golden_util import GOLDEN_DIR
 
 
+def _obstacle_variant(g):
+    """FlockingObstacle-v0: unscaled action, obstacles not actuated, velocity differences with obstacles zeroed."""
+    x = g["x0"].copy()
+    h = fnp.compute_helpers_obstacle(x, 0.9 * 0.9, 4)
+    assert np.array_equal(h["values"], g["values_0"])
+    assert np.array_equal(fnp.controller(h, 0.9, True), g["u_0"])
+    rewards = np.zeros(200)
+    for t in range(1, 201):
+        u = fnp.controller(h, 0.9, True)
+        x = fnp.integrate_leader(x, u, 0.01, 4)                         # flocking_obstacle.py:40-46 == the leader step
+        h = fnp.compute_helpers_obstacle(x, 0.9 * 0.9, 4)
+        rewards[t - 1] = fnp.instant_cost(x)
+        if t in RECORD:
+            assert np.array_equal(x, g[f"x_{t}"]), t
+            assert np.array_equal(u, g[f"u_{t}"]), t
+            assert np.array_equal(h["values"], g[f"values_{t}"]), t
+            assert np.array_equal(np.packbits(h["adj"].astype(np.uint8), axis=1), g[f"adj_{t}"]), t
+    assert np.array_equal(rewards, g["rewards"])
+    assert np.array_equal(h["adj_mean"], g["adj_mean_200"])
+
+
 def _variant_files():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "variant_*.npz")))
 
@@ -79,6 +100,8 @@ def test_numpy_port_variants_match_reference_golden(name):
     """FlockingLeader-v0 / FlockingStochastic-v0: the restated step variants reproduce the reference bit for bit."""
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     leader = "leader" in name
+    if "obstacle" in name:
+        return _obstacle_variant(g)
     x = g["x0"].copy()
     h = fnp.compute_helpers(x, 0.81)
     assert np.array_equal(h["values"], g["values_0"])
