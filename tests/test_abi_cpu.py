@@ -26,6 +26,7 @@ def test_every_declared_symbol_is_exported(L):
             "flock_ctx_step", "flock_ctx_controller", "flock_last_error"} <= names
     for n in sorted(names):
         assert hasattr(L, n), n
+    from gym_flock_b200 import _lib
     assert L.flock_abi_version() == _lib.ABI_VERSION == 3
 
 
