@@ -92,7 +92,7 @@ def test_drop_in_surface_and_synthetic_states():
         assert getattr(env, attr) == val
     assert abs(env.comm_radius2 - 0.81) < 1e-15 and isinstance(env.seed(5), list)
     assert set(gf.envs.REGISTRY) == {"Flocking-v0", "FlockingRelative-v0", "FlockingTwoFlocks-v0", "FlockingLeader-v0",
-                                        "FlockingStochastic-v0"}
+                                        "FlockingStochastic-v0", "FlockingObstacle-v0"}
     with pytest.raises(KeyError):
         gf.make("Shepherding-v0")
     a, b = initial_state(50, seed=7, min_dist=0.1), initial_states(2, 50, seed=7, min_dist=0.1)
