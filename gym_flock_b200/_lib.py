@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("FLOCK_LIB") or os.path.join(_PKG, "libflock_b200.so")
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in
-            ("flock_abi.cu", "flock_env_kernel.cuh", "flock_swarm_kernel.cuh", "flock_common.cuh")] + \
+            ("flock_abi.cu", "flock_env_kernel.cuh", "flock_swarm_kernel.cuh", "flock_reset_kernel.cuh", "flock_common.cuh")] + \
            [os.path.join(_ROOT, "include", "flock_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -102,6 +102,9 @@ def lib() -> ctypes.CDLL:
     for name in ("flock_swarm_step_f64", "flock_swarm_step_f32"):
         getattr(L, name).argtypes = step_args[:-1] + [_VP, ctypes.c_size_t, _VP]
         getattr(L, name).restype = ctypes.c_int
+    L.flock_reset_sample.argtypes = [_PP, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                     ctypes.c_int32, _VP, _VP, _VP]
+    L.flock_reset_sample.restype = ctypes.c_int
     L.flock_ctx_create.argtypes = [ctypes.POINTER(_VP), _PP, ctypes.c_int32, ctypes.c_int32]
     L.flock_ctx_create.restype = ctypes.c_int
     L.flock_ctx_destroy.argtypes = [_VP]

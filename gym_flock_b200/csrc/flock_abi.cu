@@ -13,6 +13,7 @@
 #include "../../include/flock_b200.h"
 #include "flock_env_kernel.cuh"
 #include "flock_swarm_kernel.cuh"
+#include "flock_reset_kernel.cuh"
 
 namespace {
 
@@ -330,6 +331,34 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
 
 }  // namespace
 
+int reset_sample_impl(const FlockParams *p, double r_max, double v_max, double v_bias, double min_dist, uint64_t seed,
+                      int32_t max_tries, double *x_out, int32_t *tries_out, void *stream) {
+    if (!p) return fail(FLOCK_EINVAL, "params is NULL");
+    const int E = p->n_envs, N = p->n_agents;
+    if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
+    if (!x_out) return fail(FLOCK_EINVAL, "x_out is NULL");
+    if (misaligned(x_out)) return fail(FLOCK_EALIGN, "x_out must be 16-byte aligned");
+    if (!(r_max > 0.0) || v_max < 0.0 || v_bias < 0.0 || min_dist < 0.0 || max_tries < 1)
+        return fail(FLOCK_EINVAL, "bad sampler parameters (r_max=%g v_max=%g v_bias=%g min_dist=%g max_tries=%d)", r_max, v_max,
+                    v_bias, min_dist, max_tries);
+    const size_t smem = (size_t)N * sizeof(double2);
+    const size_t smem_cap = kMaxSmem - 1024;            // the kernel also has a few static shared variables
+    if (smem > smem_cap) return fail(FLOCK_EUNSUPPORTED, "N=%d: the candidate positions do not fit one CTA's shared memory", N);
+    flock::RArgs a;
+    a.x_out = x_out; a.tries_out = tries_out; a.E = E; a.N = N; a.r_max = r_max; a.v_max = v_max; a.v_bias = v_bias;
+    a.R2 = p->comm_radius2; a.min_dist = min_dist; a.seed = seed; a.max_tries = max_tries;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(flock::flock_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        configured_dev = dev;
+    }
+    flock::flock_reset_kernel<<<E, flock::RESET_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}
+
 // ---- host-buffer context -------------------------------------------------------------------------------
 struct FlockCtx {
     FlockParams p;
@@ -397,6 +426,11 @@ int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *
                       float *values, float *network, float *reward, float *rewards_all, float *obs,
                       int32_t *final_in_b, void *stream) {
     return rollout_impl<float>(p, steps, x_a, x_b, u_a, u_b, values, network, reward, rewards_all, obs, final_in_b, stream);
+}
+
+int flock_reset_sample(const FlockParams *p, double r_max, double v_max, double v_bias, double min_dist, uint64_t seed,
+                       int32_t max_tries, double *x_out, int32_t *tries_out, void *stream) {
+    return reset_sample_impl(p, r_max, v_max, v_bias, min_dist, seed, max_tries, x_out, tries_out, stream);
 }
 
 size_t flock_swarm_scratch_bytes(const FlockParams *p) {

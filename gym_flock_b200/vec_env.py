@@ -114,6 +114,25 @@ class FlockVecEnv:
         self.elapsed = 0
         return self._observation()
 
+    def reset_random(self, seed: int = 0, r_max: float | None = None, v_max: float = 5.0, v_bias: float | None = None,
+                     min_dist: float = 0.1, max_tries: int = 200000):
+        """The reference's reset() (flocking_relative.py:156-192) for every env at once, on the device: each env draws
+        whole configurations until no pair is closer than min_dist and every agent has two neighbours
+        (flock_reset_sample: one CTA per env, Philox keyed by (seed, env)).  Defaults follow the reference's cfg path:
+        r_max = sqrt(n_agents) (:75), v_bias = v_max (:41,49).  Returns ((values|obs, network), tries[E] int32); an env
+        that found no admissible configuration has tries < 0 (the reference would loop forever there)."""
+        r_max = float(np.sqrt(self.N)) if r_max is None else float(r_max)
+        v_bias = float(v_max) if v_bias is None else float(v_bias)
+        tries = torch.zeros(self.E, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.flock_reset_sample(self._pp, r_max, float(v_max), v_bias, float(min_dist),
+                                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(max_tries),
+                                                   self._ptr(self._x[self._cur]), self._ptr(tries), self._stream()))
+        self._launch(self.x, None, None, self._u[self._cur])
+        self._u_valid = True
+        self.elapsed = 0
+        return self._observation(), tries
+
     def set_state(self, x0):
         return self.reset(x0)
 

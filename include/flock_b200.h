@@ -130,6 +130,18 @@ int flock_swarm_step_f32(const FlockParams *p, const double *x_in, const double 
                          float *network, float *reward, double *u_next, float *obs, void *scratch, size_t scratch_bytes,
                          void *stream);
 
+/* Batched reset(): the reference's rejection sampler (flocking_relative.py:156-192) for every env at once, on the device.
+ * Each env draws whole configurations -- positions uniform in the disk of radius sqrt(r_max) (:167-170), velocities
+ * U(-v_max, v_max) + a common bias U(-v_bias, v_bias)^2 (:172-174) -- until the closest pair is >= min_dist apart (0.1 in
+ * the reference, :160) and every agent has >= 2 neighbours with r2 < comm_radius2 (:164,183-184), at most max_tries times.
+ * x_out[E][N][4] (device, 16-byte aligned) receives the accepted states; tries_out[E] (device int32, nullable) the number
+ * of draws used, or -max_tries where no admissible configuration was found (x_out then holds the last draw).
+ * Counter-based generator (Philox4x32-10) keyed by (seed, env): deterministic, independent of the batch size.  Parity
+ * with the reference is statistical (same law, same acceptance test); NumPy's MT19937 stream is not reproduced.
+ * Asynchronous on `stream`; the caller runs flock_step_* (u_in = NULL) afterwards for the observation. */
+int flock_reset_sample(const FlockParams *p, double r_max, double v_max, double v_bias, double min_dist, uint64_t seed,
+                       int32_t max_tries, double *x_out, int32_t *tries_out, void *stream);
+
 /* ---- host-buffer context API (what a NumPy-only binding uses; no torch needed) ----------------
  * A context owns device buffers + pinned staging for (E, N); calls take HOST pointers, copy in,
  * launch, copy out and synchronise before returning.  dtype_bytes = 8 (f64) or 4 (f32).
