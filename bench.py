@@ -38,6 +38,8 @@ CONFIGS = {
     "C4": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64"),
     "C4x": dict(env_id="FlockingRelative-v0", E=1024, N=1000, precision="fp64-exact"),
     "C1g": dict(env_id="Flocking-v0", E=1, N=100, precision="fp64-exact"),
+    # BASELINE config 1 through the drop-in gym API (Python loop, NumPy in / out, one env): make() -> controller() -> step()
+    "C1": dict(env_id="Flocking-v0", E=1, N=100, precision="fp64-exact", dropin=True),
     "C2k": dict(env_id="Flocking-v0", E=4096, N=100, precision="fp32"),            # C2 with the kNN observation
     # single giant swarm: rows sharded over the ranks, one all-gather of the actions per step (constant density)
     "C5": dict(env_id="Flocking-v0", E=1, N=65536, precision="fp32", swarm=True),
@@ -248,7 +250,57 @@ def run_swarm(args, cfg, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_dropin(args, cfg, rank):
+    """C1: the reference's own usage pattern -- one env, a Python loop of controller() + step() -- through the drop-in
+    classes (bit-exact mode), next to the NumPy port of the reference on one host core.  Wall clock: every call returns
+    host arrays, so each step is synchronous by construction."""
+    if rank != 0:
+        return
+    import gym_flock_b200 as gf
+    from gym_flock_b200.synthetic import initial_state
+    from oracle import flock_numpy as fnp
+    N = cfg["N"]
+    K, W = max(1, args.steps), max(3, args.warmup)
+    x0 = initial_state(N, seed=1234, min_dist=0.1)
+    # reference arm first (before CUDA is touched): compute_helpers + controller + integrate (+ kNN observation)
+    t0 = time.perf_counter()
+    x = x0.copy()
+    h = fnp.compute_helpers(x, 0.81)
+    for _ in range(K):
+        u = fnp.controller(h, 0.9, True)
+        x = fnp.integrate(x, u, 0.01)
+        h = fnp.compute_helpers(x, 0.81)
+        fnp.knn_observation(x, h["r2"])
+        fnp.instant_cost(x)
+    t_ref = time.perf_counter() - t0
+    env = gf.make(cfg["env_id"])
+    raw = env.env
+    raw.set_state(x0)
+    for _ in range(W):
+        env.step(raw.controller())
+    raw.set_state(x0)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        obs, r, done, info = env.step(raw.controller())
+    t = time.perf_counter() - t0
+    same = bool(np.array_equal(raw.x, x))
+    out = {"metric": METRIC, "value": N * N * K / t, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "agent_steps_per_sec": N * K / t,
+           "config": {"workload": f"C1: {cfg['env_id']} one env x {N} agents, fp64-exact, drop-in gym API "
+                                  "(Python loop: controller() + step(), NumPy in/out)", "n_agents": N},
+           "cpu_baseline": {"value": N * N * K / t_ref, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"{K} steps, one process (oracle/flock_numpy.py)", "ms_per_step": t_ref / K * 1e3},
+           "final_state_bit_equal_to_port": same, "e2e": {"value": N * N * K / t, "unit": UNIT,
+                                                           "h2d_bytes_per_step": N * 2 * 8,
+                                                           "d2h_bytes_per_step": N * 2 * 8 + N * 4 * 8 + (N * 28 + N * N + 1) * 8},
+           "gpu_launches": K, "roofline": None}
+    print(json.dumps(out), flush=True)
+
+
 def run_ours(args, cfg, rank, world, local_rank):
+    if cfg.get("dropin"):
+        return run_dropin(args, cfg, rank)
     if cfg.get("swarm"):
         return run_swarm(args, cfg, rank, world, local_rank)
     cpu = None

@@ -10,6 +10,10 @@ pytestmark = pytest.mark.gpu
 CASES = [  # (E, N, centralized, knn, lanes)
     (8, 100, True, False, 0), (8, 100, False, True, 1), (6, 50, True, True, 4), (3, 257, True, True, 32),
     (2, 1000, True, False, 0), (4, 33, False, False, 2), (5, 7, True, True, 8), (3, 2, True, False, 0),
+    # row-expansion shapes (one thread per row): long rows with 16-byte groups (nv = 50, 33), 8-byte groups (66 -> nv 33,
+    # 130 -> nv 65), short rows handled several per iteration (N = 12, 20), partial last warp
+    (3, 200, True, False, 1), (3, 132, False, False, 1), (5, 66, True, False, 1), (2, 130, True, False, 1),
+    (40, 12, True, False, 1), (27, 20, False, False, 1),
 ]
 
 
