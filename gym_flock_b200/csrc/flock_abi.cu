@@ -116,7 +116,8 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     const size_t size_lists = (size_t)flock::MS * (W + 1) * 4;     // word-major, fixed stride, one spare word row (prefetch)
     k.off_stats = align16(k.off_masks + size_lists);
     k.off_idg = align16(k.off_stats + (size_t)GMAX * flock::STATS_PER_ENV * 8);      // 1/deg per row (in-warp row expansion)
-    pl.smem = (size_t)k.off_idg + (size_t)threads * 8;
+    k.off_obs = align16((size_t)k.off_idg + (size_t)threads * 8);                 // kNN observation rows staged per warp
+    pl.smem = (size_t)k.off_obs + (pl.knn ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0);
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
                     N, pl.smem, kMaxSmem);

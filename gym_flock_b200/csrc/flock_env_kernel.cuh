@@ -62,7 +62,7 @@ struct KArgs {
     StepVariant var;     // flocking variants (leader / stochastic); defaults reproduce FlockingRelative
     double Rm;    // fast modes: gradient mask as ONE compare r2 <= Rm (centralized: R; decentralized: also r2 < R2)
     double thrC;  // candidate threshold max(R, R2)
-    unsigned off_xs, off_pf, off_masks, off_stats, off_idg;
+    unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
     int out_mode; // dense adjacency output: 0 = zero-fill up front + the non-zeros stored over it; 1 = in-warp row expansion
     int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
 };
@@ -515,7 +515,25 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
     Acc A;
     A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
     TopK<TK> top;
-    if constexpr (KNN) top.init(i);
+    // fp32 mode, one thread per row: the running top-8 is a branch-free min/max network on packed keys -- the fp32 bits of
+    // r2 (non-negative, so they order as unsigned integers) with the low ceil(log2 N) mantissa bits replaced by the agent
+    // index.  16 VIMNMX per pair, no divergence; ties and near-ties (r2 equal to 2^-(23 - bits) relative) resolve to the
+    // lower index, the order NumPy's argsort gives equal keys.  (The compare-and-bubble insert cost ~74 instr/pair.)
+    constexpr bool KPACK = KNN && PA32 && (LANES == 1);
+    unsigned kp[TOPK];
+    unsigned kidx = 1;                                      // index mask: next power of two >= N, minus 1
+    if constexpr (KPACK) {
+        while ((int)kidx < N) kidx <<= 1;
+        kidx -= 1;
+#pragma unroll
+        for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;     // unused slot: "self", at +inf
+    } else if constexpr (KNN) {
+        top.init(i);
+    }
+    auto kp_insert = [&](unsigned k) {
+#pragma unroll
+        for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
+    };
 
     // ---- phase A: filter ----------------------------------------------------------------------------------
     // Each lane owns bit positions k = 0.. of its words; j_of(k) maps them to agents.
@@ -549,7 +567,13 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                     const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
                     bits |= (r2.x < thrA) ? (1u << (2 * tt)) : 0u;
                     bits |= (r2.y < thrA) ? (2u << (2 * tt)) : 0u;
-                    top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1);
+                    if constexpr (KPACK) {
+                        const unsigned jw = (unsigned)(2 * tbase);                       // LANES == 1: m = tbase + tt
+                        kp_insert(((__float_as_uint(r2.x) & ~kidx) | jw) + (unsigned)(2 * tt));
+                        kp_insert(((__float_as_uint(r2.y) & ~kidx) | jw) + (unsigned)(2 * tt + 1));
+                    } else {
+                        top.insert(r2.x, 2 * m); top.insert(r2.y, 2 * m + 1);
+                    }
                 };
                 if (tend == 16) {
 #pragma unroll
@@ -639,12 +663,21 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                 }
                 if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
                 nb[m] = bi;
+            } else if constexpr (KPACK) {
+                const int id = (int)(kp[m] & kidx);
+                nb[m] = (id < N) ? id : i;                   // (odd N: the pad slot at +inf is not an agent)
             } else {
                 nb[m] = top.id[m];
             }
         }
+        // One thread per row and full rows: the warp's 32 observation rows are contiguous in memory (32 x 28 values).  A
+        // lane writing its own row directly issues 28 scalar stores 112 bytes apart from its neighbours' -- partial sectors
+        // that made Flocking-v0 4x slower than FlockingRelative-v0; stage the block in shared memory and copy it out with
+        // coalesced 16-byte stores instead.
+        const bool staged = (LANES == 1) && (nre == N) && a.obs != nullptr;
+        TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
         if (valid && sub == 0 && a.obs) {
-            TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
+            TO *o = staged ? obs_w + lane * (NXS * KNN_K) : reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
             int m = 0;
             bool dropped = false;
 #pragma unroll
@@ -652,15 +685,28 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                 if (!dropped && nb[q] == i) { dropped = true; continue; }     // the diagonal (or an unused slot)
                 if (m < KNN_K) {
                     const double4 xn = xe[nb[q]];
+                    typename Tr<TO>::V4 v;
                     if constexpr (EXACT) {
-                        o[m * 4 + 0] = __dsub_rn(xi.x, xn.x); o[m * 4 + 1] = __dsub_rn(xi.y, xn.y);
-                        o[m * 4 + 2] = __dsub_rn(xi.z, xn.z); o[m * 4 + 3] = __dsub_rn(xi.w, xn.w);
+                        v.x = __dsub_rn(xi.x, xn.x); v.y = __dsub_rn(xi.y, xn.y);
+                        v.z = __dsub_rn(xi.z, xn.z); v.w = __dsub_rn(xi.w, xn.w);
                     } else {
-                        o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                        o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+                        v.x = (TO)(xi.x - xn.x); v.y = (TO)(xi.y - xn.y);
+                        v.z = (TO)(xi.z - xn.z); v.w = (TO)(xi.w - xn.w);
                     }
+                    o[m * 4 + 0] = v.x; o[m * 4 + 1] = v.y; o[m * 4 + 2] = v.z; o[m * 4 + 3] = v.w;
                     ++m;
                 }
+            }
+        }
+        if (staged) {
+            __syncwarp();
+            const int wr0 = r0 + (tid - lane);                    // first flat row of this warp == its global row
+            const int nrw = min(32, r1 - wr0);
+            if (nrw > 0) {
+                const int nvec = nrw * (NXS * KNN_K) * (int)sizeof(TO) / 16;
+                const float4 *src = reinterpret_cast<const float4 *>(obs_w);
+                float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<TO *>(a.obs) + (size_t)wr0 * (NXS * KNN_K));
+                for (int v = lane; v < nvec; v += 32) __stcs(dst + v, src[v]);
             }
         }
     }

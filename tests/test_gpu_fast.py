@@ -14,6 +14,8 @@ CASES = [  # (E, N, centralized, knn, lanes)
     # 130 -> nv 65), short rows handled several per iteration (N = 12, 20), partial last warp
     (3, 200, True, False, 1), (3, 132, False, False, 1), (5, 66, True, False, 1), (2, 130, True, False, 1),
     (40, 12, True, False, 1), (27, 20, False, False, 1),
+    # kNN with one thread per row (fp32 mode: packed-key min/max network), incl. fewer than 7 neighbours and odd N
+    (9, 100, True, True, 1), (4, 7, True, True, 1), (3, 9, False, True, 1), (2, 257, True, True, 1),
 ]
 
 
