@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     // Flocking-v0: the 7 nearest neighbours are searched among the candidates, so the candidate radius is inflated
     // (x4 in r2: ~36 candidates per row at the reference density); rows that still find fewer than 7 rescan all agents.
     const float tc = (float)a.thrC * (KNN ? 4.0f : 1.0f), rc = sqrtf(tc);
-    const float thrA = tc * (1.0f + 2e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+    const float thrA = tc * (1.0f + 3e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+    const float2 nthr2 = make_float2(-thrA, -thrA);
     unsigned *mrow = masks + (size_t)tid * a.WT;
     unsigned *lrow = lists + (size_t)rl * a.CAP;
     Acc A;
@@ -228,20 +229,23 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
         for (int w = 0; w * 16 < nsl; ++w) {
             unsigned bits = 0;
             const int qb = w * 16, qe = min(16, nsl - qb);
+            // s = dx^2 + (dy^2 - thrA): the candidate test is the SIGN of s (two packed FFMA2, no compare); one funnel
+            // shift per pair moves it into the word (first pair ends up highest: one BREV per word)
             auto body = [&](const int q) {
-                const int m = sub + LANES * (qb + q);
-                const float4 v = pe[m];
+                const float4 v = pe[sub + LANES * (qb + q)];
                 const float2 dx = __fadd2_rn(make_float2(v.x, v.y), nx);
                 const float2 dy = __fadd2_rn(make_float2(v.z, v.w), ny);
-                const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-                bits |= (r2.x <= thrA) ? (1u << (2 * q)) : 0u;
-                bits |= (r2.y <= thrA) ? (2u << (2 * q)) : 0u;
+                const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
+                bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
+                bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
             };
             if (qe == 16) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) body(q);
+                bits = __brev(bits);
             } else {
                 for (int q = 0; q < qe; ++q) body(q);
+                bits = __brev(bits) >> (32 - 2 * qe);            // 0 < qe < 16
             }
             mrow[w] = bits;
             cnt += __popc(bits);
