@@ -295,21 +295,15 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.needy_cnt = a.counters + E;
     a.needy_rows = reinterpret_cast<unsigned *>(sc + L.off_needy);
     a.E = E; a.N = N; a.NP2 = L.NP2; a.PB = L.PB; a.row_lo = row_lo; a.row_hi = row_hi;
-    a.RT = 256 / lanes;
+    a.RT = flock::SW_R * (256 / lanes);        // rows per CTA
     a.TS = 2048;
-    a.WT = (2 * ((a.TS + lanes - 1) / lanes) + 31) / 32;
-    a.CAP = 256;
     a.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
     a.R = p->comm_radius; a.R2 = p->comm_radius2; a.thrC = std::max(a.R, a.R2);
     a.Rm = (a.centralized || a.R2 > a.R) ? a.R : std::nextafter(a.R2, -1.0);
     a.dt = p->dt; a.ascale = p->action_scalar; a.inv_ascale = 1.0 / p->action_scalar; a.var = step_variant(p);
-    a.zero_bytes = 0;      // (the dense rows are zero-filled with direct stores; no shared zero block)
     a.off_tiles = 0;
-    a.off_masks = align16((size_t)2 * a.TS * 16);
-    a.off_lists = align16(a.off_masks + (size_t)256 * a.WT * 4);
-    a.off_cnt = align16(a.off_lists + (size_t)a.RT * a.CAP * 4);
-    a.off_zero = (unsigned)((a.off_cnt + (size_t)a.RT * 4 + 127) & ~(size_t)127);
-    a.off_bar = align16(a.off_zero + a.zero_bytes);
+    a.off_lists = align16((size_t)2 * a.TS * 16);                                   // [thread][SW_R][SW_LCAP] candidates
+    a.off_bar = align16(a.off_lists + (size_t)256 * flock::SW_R * flock::SW_LCAP * 4);
     const size_t smem = (size_t)a.off_bar + 16;
 
     CUDA_TRY(cudaMemsetAsync(a.counters, 0, (size_t)E * 8, st));

@@ -8,10 +8,11 @@
 //   flock_swarm_kernel (rows) : a CTA owns 256/LANES rows of one env.  The packed fp32 positions of ALL agents stream
 //                               through shared memory in tiles, double buffered with 1-D TMA bulk loads completing on
 //                               mbarriers (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes).
-//                               Per tile: phase A (packed f32x2 filter, conservative threshold) then phase B (fp64
-//                               refine of the few candidates, x_j read through L2).  Neighbours are collected in a
-//                               per-row list; the dense adj_mean rows are cleared by per-warp TMA bulk stores issued
-//                               at kernel start and the non-zeros scattered at the end.   :111-134,194-226, flocking.py:20-24
+//                               Per tile: phase A (packed f32x2 filter, conservative threshold, two rows per thread)
+//                               appends the few candidates to per-thread lists; after the last tile phase B refines
+//                               them in fp64 (x_j read through L2).  The dense adj_mean rows are zero-filled by the
+//                               owning warp with direct streaming stores, one slice per tile, and the non-zeros are
+//                               stored over them at the end.                     :111-134,194-226, flocking.py:20-24
 //
 // The row arithmetic does not depend on how rows are sharded over CTAs or GPUs.  Exact-order (NumPy bit-exact) mode
 // is not offered here: its sequential all-j sums belong to the env-resident kernel (N up to a few thousand).
@@ -37,15 +38,12 @@ struct SArgs {
     unsigned *needy_rows;   // scratch: [E][NEEDY_CAP]
     int E, N, NP2, PB;
     int row_lo, row_hi;
-    int RT;                 // rows per CTA (256 / LANES)
+    int RT;                 // rows per CTA (SW_R * 256 / LANES)
     int TS;                 // pair slots per tile
-    int WT;                 // 32-bit candidate words per (thread, tile)
-    int CAP;                // neighbour-list capacity per row
     int centralized;
     double R, R2, Rm, thrC, dt, ascale, inv_ascale;
     StepVariant var;
-    unsigned off_tiles, off_masks, off_lists, off_cnt, off_zero, off_bar;
-    unsigned zero_bytes;
+    unsigned off_tiles, off_lists, off_bar;
 };
 
 constexpr int PREP_THREADS = 256;
@@ -130,35 +128,44 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a,
 }
 
 // ---- the row kernel --------------------------------------------------------------------------------------------------
+// A CTA owns SW_R * 256/LANES consecutive rows of one env: thread (rl, sub) works for rows SW_R*rl .. SW_R*rl + SW_R-1.
+//   tile loop : every packed slot loaded from shared memory (one LDS.128) is tested against the thread's SW_R rows --
+//               per row 2 FADD2 + 2 FFMA2 + 2 funnel shifts, the candidate test is the sign of dx^2 + (dy^2 - thr) --
+//               so the loop is ALU bound with SW_R independent chains per load (with one row per thread it stalled on
+//               the LDS latency at 4 warps per scheduler: 47 % issue utilisation).  The rare candidates (a few per row
+//               and tile) are appended, ascending j, to the thread's own list in shared memory: no atomics, no order
+//               that depends on timing.
+//   refine    : after the last tile each thread refines the candidates of its lists in fp64 (x_j through L2), row by
+//               row; the LANES partial sums of a row are combined with xor shuffles.  Per-lane ascending j plus a fixed
+//               shuffle pattern: the result does not depend on how rows are sharded over CTAs or GPUs.
+//   overflow  : a (row, lane) list holds SW_LCAP candidates; a row with a fuller list (a swarm far denser than the
+//               reference's) is recomputed by scanning all agents.
+constexpr int SW_R = 2;         // rows per thread in the filter
+constexpr int SW_LCAP = 16;     // candidates per (row, lane)
+
 template <typename TO, int LANES, bool KNN>
 __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     static_assert(LANES >= 8 && LANES <= 32, "swarm rows are split over 8..32 lanes");
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *tiles = reinterpret_cast<float4 *>(smem + a.off_tiles);          // 2 stages x TS slots
-    unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);      // [thread][WT]
-    unsigned *lists = reinterpret_cast<unsigned *>(smem + a.off_lists);      // [row][CAP] neighbour indices
-    int *lcnt = reinterpret_cast<int *>(smem + a.off_cnt);                   // [row] neighbours found (may exceed CAP)
+    unsigned *lists = reinterpret_cast<unsigned *>(smem + a.off_lists);      // [thread][SW_R][SW_LCAP] candidate indices
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + a.off_bar);   // 2 mbarriers
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int env = blockIdx.y;
     const int N = a.N, NP2 = a.NP2;
     const int rl = tid / LANES, sub = tid % LANES;
-    const int i = a.row_lo + blockIdx.x * a.RT + rl;
-    const bool valid = (rl < a.RT) && (i < a.row_hi);
+    const int RTC = SW_R * (256 / LANES);                                    // rows per CTA
+    const int ibase = a.row_lo + blockIdx.x * RTC + rl * SW_R;               // first row of this thread
     const size_t e0 = (size_t)env * N;
     const double *xc = a.x_cur + e0 * 4;
     const float4 *pfe = a.pf + (size_t)env * NP2;
     TO *net = reinterpret_cast<TO *>(a.network);
-    const size_t grow = e0 + (valid ? i : a.row_lo);
     const int ntiles = (NP2 + a.TS - 1) / a.TS;
 
-    // ---- setup: zero block, list counters, barriers; first two tiles in flight -----------------------------------------
-    {
-        for (int q = tid; q < a.RT; q += blockDim.x) lcnt[q] = 0;
-        if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-        fence_async_smem();
-    }
+    // ---- setup: barriers; first two tiles in flight ------------------------------------------------------------------
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    fence_async_smem();
     __syncthreads();
     auto issue_tile = [&](const int t) {                                     // one thread: queue tile t into stage t&1
         const int s0 = t * a.TS, ns = min(a.TS, NP2 - s0);
@@ -169,12 +176,12 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
 
     // ---- zero-fill of the warp's rows of the dense adjacency: plain coalesced 16-byte streaming stores, one slice per
     //      tile of the main loop, so the writes drain to HBM while the warp filters.  (1-D TMA bulk stores from a shared
-    //      zero block were measured slower: the bulk-store queue throttles at ~3.6-4.8 TB/s, direct stores reach 6.3.)
+    //      zero block were measured slower, and so is any scheme that writes a sector twice.)
     float4 *zdst = nullptr;                                  // first 16-byte vector of the warp's region
     size_t znvec = 0;
     if (net) {
-        const int wr0 = a.row_lo + blockIdx.x * a.RT + (tid - lane) / LANES;    // first row of this warp
-        const int wr1 = min(min(wr0 + 32 / LANES, a.row_lo + (int)(blockIdx.x + 1) * a.RT), a.row_hi);
+        const int wr0 = a.row_lo + blockIdx.x * RTC + ((tid - lane) / LANES) * SW_R;     // first row of this warp
+        const int wr1 = min(min(wr0 + (32 / LANES) * SW_R, a.row_lo + (int)(blockIdx.x + 1) * RTC), a.row_hi);
         if (wr0 < wr1) {
             const size_t base = (e0 + wr0) * (size_t)N;
             const size_t total = (size_t)(wr1 - wr0) * N;
@@ -199,76 +206,75 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
         for (; v < hi; v += 32) __stcs(zdst + v, z4);
     };
 
-    // ---- row state ------------------------------------------------------------------------------------------------------
-    const double4 xi = ld_state(xc + (size_t)(valid ? i : a.row_lo) * 4);
+    // ---- per-row filter state ----------------------------------------------------------------------------------------
     const double *tot = a.totals + (size_t)env * 8;
-    const float pxi = (float)(xi.x - tot[5]), pyi = (float)(xi.y - tot[6]);     // same rounding as the packed array
-    const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
     // Flocking-v0: the 7 nearest neighbours are searched among the candidates, so the candidate radius is inflated
     // (x4 in r2: ~36 candidates per row at the reference density); rows that still find fewer than 7 rescan all agents.
     const float tc = (float)a.thrC * (KNN ? 4.0f : 1.0f), rc = sqrtf(tc);
-    const float thrA = tc * (1.0f + 3e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
-    const float2 nthr2 = make_float2(-thrA, -thrA);
-    unsigned *mrow = masks + (size_t)tid * a.WT;
-    unsigned *lrow = lists + (size_t)rl * a.CAP;
-    Acc A;
-    A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
-    TopK<double> top;                                       // kNN by exact fp64 r2 over the candidates
-    if constexpr (KNN) top.init(i);
-    const bool cen = a.centralized != 0;
+    bool valid[SW_R];
+    float2 nx[SW_R], ny[SW_R], nthr[SW_R];
+    int cn[SW_R];                                            // candidates of this thread per row (may exceed SW_LCAP)
+    unsigned *lst[SW_R];
+#pragma unroll
+    for (int r = 0; r < SW_R; ++r) {
+        const int i = ibase + r;
+        valid[r] = (i < a.row_hi) && (i < a.row_lo + (int)(blockIdx.x + 1) * RTC);
+        const double2 pi_ = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)(valid[r] ? i : a.row_lo) * 4));
+        const float pxi = (float)(pi_.x - tot[5]), pyi = (float)(pi_.y - tot[6]);   // same rounding as the packed array
+        nx[r] = make_float2(-pxi, -pxi); ny[r] = make_float2(-pyi, -pyi);
+        const float thrA = tc * (1.0f + 3e-6f) + 16.0f * rc * (fmaxf(fabsf(pxi), fabsf(pyi)) + 2.0f * rc) * 5.9604645e-8f;
+        nthr[r] = make_float2(-thrA, -thrA);
+        cn[r] = 0;
+        lst[r] = lists + ((size_t)tid * SW_R + r) * SW_LCAP;
+    }
 
-    // ---- stream the tiles ------------------------------------------------------------------------------------------------
+    // ---- stream the tiles: filter only ---------------------------------------------------------------------------------
     for (int t = 0; t < ntiles; ++t) {
         const int s0 = t * a.TS, ns = min(a.TS, NP2 - s0);
         if (znvec) zero_slice(t);                            // queued before the wait: drains while the tile is filtered
         mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
         const float4 *pe = tiles + (size_t)(t & 1) * a.TS;
-        // phase A on this tile: slots sub, sub+LANES, ... ; bit 2q / 2q+1 of the lane's words = the slot's two agents
-        const int nsl = valid ? (ns - sub + LANES - 1) / LANES : 0;
-        int cnt = 0;
+        // slots sub, sub+LANES, ... ; bit 2q / 2q+1 of a word = the two agents of the word's q-th slot
+        const int nsl = (ns - sub + LANES - 1) / LANES;
         for (int w = 0; w * 16 < nsl; ++w) {
-            unsigned bits = 0;
+            unsigned bits[SW_R];
+#pragma unroll
+            for (int r = 0; r < SW_R; ++r) bits[r] = 0;
             const int qb = w * 16, qe = min(16, nsl - qb);
             // s = dx^2 + (dy^2 - thrA): the candidate test is the SIGN of s (two packed FFMA2, no compare); one funnel
             // shift per pair moves it into the word (first pair ends up highest: one BREV per word)
             auto body = [&](const int q) {
                 const float4 v = pe[sub + LANES * (qb + q)];
-                const float2 dx = __fadd2_rn(make_float2(v.x, v.y), nx);
-                const float2 dy = __fadd2_rn(make_float2(v.z, v.w), ny);
-                const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
-                bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
-                bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+#pragma unroll
+                for (int r = 0; r < SW_R; ++r) {
+                    const float2 dx = __fadd2_rn(make_float2(v.x, v.y), nx[r]);
+                    const float2 dy = __fadd2_rn(make_float2(v.z, v.w), ny[r]);
+                    const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr[r]));
+                    bits[r] = __funnelshift_l(__float_as_uint(s.x), bits[r], 1);
+                    bits[r] = __funnelshift_l(__float_as_uint(s.y), bits[r], 1);
+                }
             };
             if (qe == 16) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) body(q);
-                bits = __brev(bits);
+#pragma unroll
+                for (int r = 0; r < SW_R; ++r) bits[r] = __brev(bits[r]);
             } else {
                 for (int q = 0; q < qe; ++q) body(q);
-                bits = __brev(bits) >> (32 - 2 * qe);            // 0 < qe < 16
+#pragma unroll
+                for (int r = 0; r < SW_R; ++r) bits[r] = __brev(bits[r]) >> (32 - 2 * qe);   // 0 < qe < 16
             }
-            mrow[w] = bits;
-            cnt += __popc(bits);
-        }
-        // phase B on this tile's candidates (x_j through L2); neighbours go to the row's list
-        {
-            int w = -1;
-            unsigned cand = 0;
-            for (int c = 0; c < cnt; ++c) {
-                while (cand == 0) { ++w; cand = mrow[w]; }
-                const int k = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const int kk = w * 32 + k;
-                const int j = 2 * (s0 + sub + LANES * (kk >> 1)) + (kk & 1);
-                if (j == i || j >= N) continue;
-                const double4 xj = ld_state(xc + (size_t)j * 4);
-                if constexpr (KNN) {
-                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
-                    top.insert(fma(dx, dx, dy * dy), j);
-                }
-                if (refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) {
-                    const int pos = atomicAdd(&lcnt[rl], 1);
-                    if (pos < a.CAP) lrow[pos] = (unsigned)j;
+            // the rare candidates go to the thread's lists, ascending j
+#pragma unroll
+            for (int r = 0; r < SW_R; ++r) {
+                unsigned c = valid[r] ? bits[r] : 0u;
+                while (c) {
+                    const int k = __ffs(c) - 1;
+                    c &= c - 1;
+                    const int j = 2 * (s0 + sub + LANES * (qb + (k >> 1))) + (k & 1);
+                    if (j == ibase + r || j >= N) continue;
+                    if (cn[r] < SW_LCAP) lst[r][cn[r]] = (unsigned)j;
+                    ++cn[r];
                 }
             }
         }
@@ -276,109 +282,151 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
         if (tid == 0 && t + 2 < ntiles) issue_tile(t + 2);
     }
 
-    // ---- reduce across the LANES threads of a row ----------------------------------------------------------------------
+    // ---- refine, row by row (the lists are private to the thread: no barrier needed) ------------------------------------
+    const bool cen = a.centralized != 0;
+#pragma unroll 1
+    for (int r = 0; r < SW_R; ++r) {
+        const int i = valid[r] ? ibase + r : a.row_lo;
+        const size_t grow = e0 + i;
+        const double4 xi = ld_state(xc + (size_t)i * 4);
+        Acc A;
+        A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
+        TopK<double> top;                                    // kNN by exact fp64 r2 over the candidates
+        if constexpr (KNN) top.init(i);
+        int deg = 0;
+        // a list that overflowed anywhere in the row: the whole row is recomputed from all agents (same on every lane)
+        bool over = valid[r] && cn[r] > SW_LCAP;
 #pragma unroll
-    for (int m = LANES / 2; m > 0; m >>= 1) {
-        A.f0 += shfl_xor(A.f0, m); A.f1 += shfl_xor(A.f1, m); A.f2 += shfl_xor(A.f2, m);
-        A.f3 += shfl_xor(A.f3, m); A.f4 += shfl_xor(A.f4, m); A.f5 += shfl_xor(A.f5, m);
-        A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
-    }
-    const int deg = valid ? lcnt[rl] : 0;                    // complete: the last tile ended with a block barrier
-    TO idg;
-    if constexpr (sizeof(TO) == 4) idg = __frcp_rn((float)max(deg, 1));
-    else idg = Tr<double>::rcp((double)max(deg, 1));
-
-    if (valid && sub == 0) {
-        if (a.values) {
-            TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
-            v[0] = (TO)A.f0; v[1] = (TO)A.f1; v[2] = (TO)A.f2; v[3] = (TO)A.f3; v[4] = (TO)A.f4; v[5] = (TO)A.f5;
-        }
-        if (a.u_next) {
-            double sdx = A.f0, sdy = A.f3;
-            if (cen) {                                       // sum_j (v_i - v_j) = N*(v_i - ref) - sum_j (v_j - ref)
-                sdx = fma((double)N, xi.z - tot[0], -tot[2]);
-                sdy = fma((double)N, xi.w - tot[1], -tot[3]);
-            }
-            double ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * a.inv_ascale;
-            double uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * a.inv_ascale;
-            if (a.var.u_clip > 0.0) {
-                ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
-            }
-            reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
-        }
-    }
-
-    // ---- kNN observation ------------------------------------------------------------------------------------------------
-    if constexpr (KNN) {
-        int nb[TOPK];
-        auto merge = [&](int *out) {                         // every lane of the row ends with the row's sorted ids
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) {
-                double bd = top.d[0]; int bi = top.id[0];
-#pragma unroll
-                for (int s = LANES / 2; s > 0; s >>= 1) {
-                    const double od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
-                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-                }
-                if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
-                out[m] = bi;
-            }
-        };
-        merge(nb);
-        // Fewer than 7 neighbours inside the inflated radius (flock edge, stray agents): the row is queued for
-        // flock_knn_fix_kernel, which rescans ALL agents with a whole CTA per row after this kernel (so the few such
-        // rows do not stretch this kernel's tail).  If the queue is full the row rescans here.
-        bool need = valid && (nb[KNN_K - 1] == i);
-        if (need && a.obs) {
-            unsigned slot = 0;
-            if (sub == 0) slot = atomicAdd(a.needy_cnt + env, 1u);
-            slot = __shfl_sync(__activemask(), slot, (lane / LANES) * LANES);
-            if (slot < (unsigned)NEEDY_CAP) {
-                if (sub == 0) a.needy_rows[(size_t)env * NEEDY_CAP + slot] = (unsigned)i;
-                need = false;
-            }
-        }
-        if (__any_sync(0xffffffffu, need)) {
-            top.init(i);
-            if (need) {
-                for (int j = sub; j < N; j += LANES) {
-                    if (j == i) continue;
-                    const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
-                    const double dx = xi.x - pj.x, dy = xi.y - pj.y;
+        for (int m = LANES / 2; m > 0; m >>= 1) over |= (__shfl_xor_sync(0xffffffffu, over ? 1 : 0, m) != 0);
+        const int ncand = valid[r] ? min(cn[r], SW_LCAP) : 0;
+        if (!over) {
+            for (int c = 0; c < ncand; ++c) {
+                const int j = (int)lst[r][c];
+                const double4 xj = ld_state(xc + (size_t)j * 4);
+                if constexpr (KNN) {
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
                     top.insert(fma(dx, dx, dy * dy), j);
                 }
+                if (refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) { lst[r][c] = (unsigned)j | 0x80000000u; ++deg; }
             }
-            int nb2[TOPK];
-            merge(nb2);
-            if (need) {
-#pragma unroll
-                for (int m = 0; m < TOPK; ++m) nb[m] = nb2[m];
-            }
-        }
-        if (valid && sub == 0 && a.obs) {
-            TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
-#pragma unroll
-            for (int m = 0; m < KNN_K; ++m) {                 // the diagonal is never a candidate here; unused slots hold i
-                const double4 xn = ld_state(xc + (size_t)min(nb[m], N - 1) * 4);
-                o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
-            }
-        }
-    }
-
-    // ---- scatter the non-zero adj_mean entries -------------------------------------------------------------------------
-    if (net == nullptr) return;
-    __syncwarp();                                            // the warp's zero stores precede its non-zero stores
-    if (valid) {
-        TO *orow = net + grow * N;
-        if (deg <= a.CAP) {
-            for (int c = sub; c < deg; c += LANES) orow[lrow[c]] = idg;
-        } else {                                             // rare: denser than the list; recompute the row's adjacency
+        } else if (valid[r]) {
             for (int j = sub; j < N; j += LANES) {
                 if (j == i) continue;
-                const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
-                const double dx = xi.x - pj.x, dy = xi.y - pj.y;
-                if (fma(dx, dx, dy * dy) < a.R2) orow[j] = idg;
+                const double4 xj = ld_state(xc + (size_t)j * 4);
+                const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                const double r2 = fma(dx, dx, dy * dy);
+                if constexpr (KNN) top.insert(r2, j);
+                if (r2 <= a.thrC && refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) ++deg;
+            }
+        }
+        // reduce across the LANES threads of the row
+#pragma unroll
+        for (int m = LANES / 2; m > 0; m >>= 1) {
+            A.f0 += shfl_xor(A.f0, m); A.f1 += shfl_xor(A.f1, m); A.f2 += shfl_xor(A.f2, m);
+            A.f3 += shfl_xor(A.f3, m); A.f4 += shfl_xor(A.f4, m); A.f5 += shfl_xor(A.f5, m);
+            A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
+            deg += shfl_xor(deg, m);
+        }
+        TO idg;
+        if constexpr (sizeof(TO) == 4) idg = __frcp_rn((float)max(deg, 1));
+        else idg = Tr<double>::rcp((double)max(deg, 1));
+
+        if (valid[r] && sub == 0) {
+            if (a.values) {
+                TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
+                v[0] = (TO)A.f0; v[1] = (TO)A.f1; v[2] = (TO)A.f2; v[3] = (TO)A.f3; v[4] = (TO)A.f4; v[5] = (TO)A.f5;
+            }
+            if (a.u_next) {
+                double sdx = A.f0, sdy = A.f3;
+                if (cen) {                                   // sum_j (v_i - v_j) = N*(v_i - ref) - sum_j (v_j - ref)
+                    sdx = fma((double)N, xi.z - tot[0], -tot[2]);
+                    sdy = fma((double)N, xi.w - tot[1], -tot[3]);
+                }
+                double ux = fmin(fmax(-2.0 * A.gx - sdx, -10.0), 10.0) * a.inv_ascale;
+                double uy = fmin(fmax(-sdy - 2.0 * A.gy, -10.0), 10.0) * a.inv_ascale;
+                if (a.var.u_clip > 0.0) {
+                    ux = fmin(fmax(ux, -a.var.u_clip), a.var.u_clip); uy = fmin(fmax(uy, -a.var.u_clip), a.var.u_clip);
+                }
+                reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
+            }
+        }
+
+        // ---- kNN observation ------------------------------------------------------------------------------------------
+        if constexpr (KNN) {
+            int nb[TOPK];
+            auto merge = [&](int *out) {                     // every lane of the row ends with the row's sorted ids
+#pragma unroll
+                for (int m = 0; m < TOPK; ++m) {
+                    double bd = top.d[0]; int bi = top.id[0];
+#pragma unroll
+                    for (int s2 = LANES / 2; s2 > 0; s2 >>= 1) {
+                        const double od = shfl_xor(bd, s2); const int oi = shfl_xor(bi, s2);
+                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                    }
+                    if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
+                    out[m] = bi;
+                }
+            };
+            merge(nb);
+            // Fewer than 7 neighbours inside the inflated radius (flock edge, stray agents): the row is queued for
+            // flock_knn_fix_kernel, which rescans ALL agents with a whole CTA per row after this kernel (so the few such
+            // rows do not stretch this kernel's tail).  If the queue is full the row rescans here.
+            bool need = valid[r] && !over && (nb[KNN_K - 1] == i);
+            if (need && a.obs) {
+                unsigned slot = 0;
+                if (sub == 0) slot = atomicAdd(a.needy_cnt + env, 1u);
+                slot = __shfl_sync(__activemask(), slot, (lane / LANES) * LANES);
+                if (slot < (unsigned)NEEDY_CAP) {
+                    if (sub == 0) a.needy_rows[(size_t)env * NEEDY_CAP + slot] = (unsigned)i;
+                    need = false;
+                }
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                top.init(i);
+                if (need) {
+                    for (int j = sub; j < N; j += LANES) {
+                        if (j == i) continue;
+                        const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
+                        const double dx = xi.x - pj.x, dy = xi.y - pj.y;
+                        top.insert(fma(dx, dx, dy * dy), j);
+                    }
+                }
+                int nb2[TOPK];
+                merge(nb2);
+                if (need) {
+#pragma unroll
+                    for (int m = 0; m < TOPK; ++m) nb[m] = nb2[m];
+                }
+            }
+            if (valid[r] && sub == 0 && a.obs) {
+                TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
+#pragma unroll
+                for (int m = 0; m < KNN_K; ++m) {             // the diagonal is never a candidate here; unused slots hold i
+                    const double4 xn = ld_state(xc + (size_t)min(nb[m], N - 1) * 4);
+                    o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                    o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+                }
+            }
+        }
+
+        // ---- the non-zero adj_mean entries, over the warp's zero-filled rows -----------------------------------------------
+        if (net != nullptr) {
+            __syncwarp();                                    // the warp's zero stores precede its non-zero stores
+            if (valid[r]) {
+                TO *orow = net + grow * N;
+                if (!over) {
+                    for (int c = 0; c < ncand; ++c) {
+                        const unsigned e = lst[r][c];
+                        if (e & 0x80000000u) orow[e & 0x7fffffffu] = idg;
+                    }
+                } else {                                     // rare: recompute the row's adjacency
+                    for (int j = sub; j < N; j += LANES) {
+                        if (j == i) continue;
+                        const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
+                        const double dx = xi.x - pj.x, dy = xi.y - pj.y;
+                        if (fma(dx, dx, dy * dy) < a.R2) orow[j] = idg;
+                    }
+                }
             }
         }
     }

@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_swarm.py -x -q 2>&1 | tail -3
+python -m pytest tests/test_gpu_swarm.py -x -q 2>&1 | tail -5
 for ADJ in dense none; do
 python bench.py --config C5 --steps 20 --warmup 3 --adjacency $ADJ 2>&1 | python -c "
 import json,sys
