@@ -157,9 +157,12 @@ def run_reference(args, cfg, rank):
         return
     steps = max(1, args.steps)
     N = cfg["N"]
-    per = max(1, min(4, int(4.0e8 / (N * N * (steps + args.warmup) * 1.0)) or 1))
-    # warm-up steps are folded into the pool warm-up; each "step" is one lockstep step of the sample
-    rate, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=per, steps=steps)
+    # Each "step" is one lockstep step of a bounded sample of the workload: as many envs per core as keep the whole run
+    # at ~15 s of CPU work (about 6.5e6 pair-interactions/s per core at N=100), at most the config's own batch.  The
+    # warm-up steps are folded into the pool warm-up (imports, page-in).
+    ncores = os.cpu_count() or 1
+    per = max(1, min(max(1, cfg["E"] // ncores), int(9.0e7 / (N * N * steps)) or 1))
+    rate, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=per, steps=steps, pairs_per_core=9.0e7)
     E_s = per * cores
     out = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
