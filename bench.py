@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-gather", type=int, default=0, help="C5 diagnostic: skip the all-gather (results wrong; timing only)")
-    ap.add_argument("--lanes", type=int, default=16, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
+    ap.add_argument("--lanes", type=int, default=32, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
     ap.add_argument("--env-lanes", type=int, default=0, help="env batches: threads per row (0 = library heuristic)")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")

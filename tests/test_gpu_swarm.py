@@ -120,3 +120,26 @@ def test_streaming_swarm_sparse_rows_use_knn_fixup(precision):
     assert (err <= tol).all(), (int((err > tol).sum()), float(err.max()))
     h = c_oracle.helpers(x0)
     assert np.array_equal(net.cpu().numpy() > 0, h["adj_mean"] > 0)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_streaming_swarm_dense_rows_overflow_the_candidate_lists(precision):
+    """A swarm far denser than the reference's (every row has more candidates inside the inflated radius than its
+    per-lane lists hold): the row kernel's full-scan fallback runs for every row.  Same parity bars as everywhere else."""
+    import torch
+    from gym_flock_b200 import SwarmEnv
+    from gym_flock_b200.synthetic import initial_state
+    from parity_util import check_pass
+    from oracle import c_oracle
+    n = 800
+    x0 = initial_state(n, seed=800, law="density", density=177.0, min_dist=0.05)      # disk of radius 1.2
+    d = x0[:, None, :2] - x0[None, :, :2]
+    r2 = (d * d).sum(-1)
+    assert ((r2 <= 3.6).sum(1) - 1).min() > 16 * 32       # more candidates per row than 32 lanes x 16 entries
+    sw = SwarmEnv("Flocking-v0", n_agents=n, precision=precision, streaming=True)
+    obs, net = sw.reset(x0)
+    torch.cuda.synchronize()
+    check_pass(x0, sw.values.cpu().numpy(), net.cpu().numpy(), sw.u.cpu().numpy(), float(sw.reward), precision)
+    ref_obs = c_oracle.knn_obs(x0)
+    same = np.isclose(obs.cpu().numpy(), ref_obs, rtol=0, atol=1e-4 if precision == "fp32" else 1e-9).all(axis=1)
+    assert same.mean() > 0.98
