@@ -338,7 +338,7 @@ __device__ __forceinline__ Win window_of(const KArgs &a, const int w) {
 
 // the locals every phase of a window uses (unused ones cost nothing)
 #define FLOCK_WIN_LOCALS                                                                                         \
-    constexpr bool PA32 = std::is_same<TO, float>::value; /* phase A on packed fp32 positions */                \
+    [[maybe_unused]] constexpr bool PA32 = std::is_same<TO, float>::value; /* phase A on packed fp32 */                \
     [[maybe_unused]] double4 *xs = reinterpret_cast<double4 *>(smem + a.off_xs);                                  \
     [[maybe_unused]] float4 *pf = reinterpret_cast<float4 *>(smem + a.off_pf); /* (px_2m, px_2m+1, py_2m, py_2m+1) - env origin */ \
     [[maybe_unused]] double *stats = reinterpret_cast<double *>(smem + a.off_stats);                              \
