@@ -5,20 +5,22 @@
 // the environments its rows belong to in shared memory.  Each ordered pair (i,j) is visited exactly once per
 // step.  After ONE block barrier (state staged) every warp runs on its own:
 //
-//   zero-fill : lane 0 queues 1-D bulk (TMA) stores of a shared zero block over the warp's slice of the dense
-//               adj_mean output; the copy engine streams them to HBM while the warp computes
 //   prologue  : x' = integrate(x_in, u_in)                          flocking_relative.py:96-105
 //               reward = -(var vx' + var vy')                       flocking_relative.py:145-147
-//   phase A   : FILTER over all N^2 ordered pairs: r2 and one compare per pair, candidate bits
-//               (r2 <= max(R, R^2)) kept in shared memory.          flocking_relative.py:113-117
-//               fp32 output mode: packed f32x2 math on fp32 positions relative to a per-env origin with a
-//               conservative per-row threshold; fp64 modes: fp64 r2 (exact mode: NumPy's unfused r2).
+//   phase A   : FILTER over all N^2 ordered pairs, candidate bits (r2 <= max(R, R^2)) kept in shared memory, word-major.
+//               fp32 output mode: packed f32x2 math on fp32 positions relative to a per-env origin; the test is the
+//               SIGN of dx^2 + (dy^2 - thr) with a conservative per-row threshold, shifted into the word (no compare).
+//               fp64 modes: fp64 r2 (exact mode: NumPy's unfused r2).         flocking_relative.py:113-117
 //               Flocking-v0: a running top-8 by r2 rides along.     flocking.py:20-24
-//   phase B   : REFINE only the candidates (~deg of N) in fp64: exact adjacency bit, the 6 masked
-//               feature sums, the potential gradient.               flocking_relative.py:117-129,214-226
+//   phase B   : REFINE only the candidates (~deg of N) in fp64, branch-free in the fast modes: exact adjacency bit
+//               (cleared in place when the candidate is no neighbour), the 6 masked feature sums, the potential
+//               gradient.                                           flocking_relative.py:117-129,214-226
 //               EXACT: NumPy's operation order, separately rounded, IEEE divide, ascending j.
-//   epilogue  : values, u_next (clip, /10), obs; after the warp's bulk zero stores have completed, the few
-//               non-zero adj_mean entries (1/deg) are scattered into its rows.   flocking_relative.py:120-122,209-211
+//   epilogue  : values, u_next (clip, /10), obs (staged per warp, stored coalesced).   flocking_relative.py:120-122,209-211
+//   dense rows: one thread per row and full rows: every warp expands its 32 rows of adj_mean from the exact bit masks
+//               with coalesced 16-byte streaming stores -- every byte written exactly once (partial-sector writes,
+//               not the store path, are what made "zero-fill + scatter" slow).  Otherwise (sharded rows, several
+//               lanes per row): zero-fill with the same stores up front, the non-zeros stored over them at the end.
 //
 // Non-neighbour pairs contribute exact zeros to every masked sum of the reference, so skipping them in
 // phase B changes nothing (not even in EXACT mode, up to the sign of a zero).  The centralized alignment
