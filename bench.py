@@ -161,8 +161,9 @@ def run_reference(args, cfg, rank):
     # at ~15 s of CPU work (about 6.5e6 pair-interactions/s per core at N=100), at most the config's own batch.  The
     # warm-up steps are folded into the pool warm-up (imports, page-in).
     ncores = os.cpu_count() or 1
-    per = max(1, min(max(1, cfg["E"] // ncores), int(9.0e7 / (N * N * steps)) or 1))
-    rate, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=per, steps=steps, pairs_per_core=9.0e7)
+    budget = float(os.environ.get("FLOCK_BENCH_REF_PAIRS_PER_CORE", "9.0e7"))      # (tests shrink the sample)
+    per = max(1, min(max(1, cfg["E"] // ncores), int(budget / (N * N * steps)) or 1))
+    rate, dt, sample, cores = cpu_numpy_port(cfg, envs_per_core=per, steps=steps, pairs_per_core=budget)
     E_s = per * cores
     out = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
