@@ -1,6 +1,6 @@
 // flock_abi.cu -- extern "C" boundary of libflock_b200.so (declared in include/flock_b200.h).
-// Host-side planning (how rows map to CTAs / lanes / shared memory) and kernel dispatch live here;
-// no torch or C++ types cross the ABI.
+// Host-side planning (which kernel, how rows map to CTAs / lanes / shared memory) lives here; the kernel
+// instantiations are in launch_*.cu.  No torch or C++ types cross the ABI.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -10,14 +10,30 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/flock_b200.h"
-#include "flock_env_kernel.cuh"
+#define FLOCK_ARGS_ONLY 1      // argument structs and constants of the kernels, not their device code
+#include "flock_host.hpp"
+#include "flock_group_kernel.cuh"
 #include "flock_swarm_kernel.cuh"
 #include "flock_reset_kernel.cuh"
+#include "flock_graph_kernels.cuh"
+
+namespace {
+thread_local std::string g_err;
+}
+
+int flock_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 
 namespace {
 
-thread_local std::string g_err;
+#define fail flock_fail
 
 flock::StepVariant step_variant(const FlockParams *p) {
     flock::StepVariant v;
@@ -29,37 +45,29 @@ flock::StepVariant step_variant(const FlockParams *p) {
     return v;
 }
 
-int fail(int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
-}
-
-#define CUDA_TRY(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess) return fail(FLOCK_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));   \
-    } while (0)
-
-constexpr int kSMs = 148;
-constexpr size_t kMaxSmem = 227 * 1024;
-
 inline unsigned align16(size_t v) { return (unsigned)((v + 15) & ~(size_t)15); }
 inline int round_up32(int v) { return (v + 31) & ~31; }
 
+// diagnostics word (FlockParams.reserved): bits 0-7 CTA size / 32 of the env kernel, bits 8-15 phase switches of the env
+// kernel, bits 16-23 envs per CTA of the group kernel, bit 24 never use the group kernel, bit 25 no programmatic dependent
+// launch, bit 26 flock_rollout_* queues single-step launches instead of one fused launch
+inline int tune_threads(const FlockParams *p) { return p->reserved & 0xff; }
+inline int tune_phases(const FlockParams *p) { return (p->reserved >> 8) & 0xff; }
+inline int tune_group(const FlockParams *p) { return (p->reserved >> 16) & 0xff; }
+inline bool tune_no_group(const FlockParams *p) { return (p->reserved >> 24) & 1; }
+inline bool tune_no_pdl(const FlockParams *p) { return (p->reserved >> 25) & 1; }
+inline bool tune_no_fuse(const FlockParams *p) { return (p->reserved >> 26) & 1; }
+
 struct Plan {
+    bool group;               // flock_group_kernel (whole envs per CTA) instead of flock_env_kernel
     flock::KArgs k;
+    flock::GArgs g;
     int lanes, threads, grid;
     size_t smem;
     bool exact, knn;
 };
 
-// Decide lanes-per-row, envs-per-CTA (or rows-per-tile) and the shared-memory layout.
-int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
+int validate(const FlockParams *p, int tbytes, int &row_lo, int &row_hi) {
     if (!p) return fail(FLOCK_EINVAL, "params is NULL");
     const int E = p->n_envs, N = p->n_agents;
     if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
@@ -67,34 +75,113 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         return fail(FLOCK_EINVAL, "bad variant parameters (n_leaders=%d n_obstacles=%d u_clip=%g state_scale=%g)", p->n_leaders,
                     p->n_obstacles, p->u_clip, p->state_scale);
     if ((long long)E * N > (1LL << 30)) return fail(FLOCK_EUNSUPPORTED, "E*N too large");
-    int row_lo = p->row_lo, row_hi = p->row_hi;
+    row_lo = p->row_lo; row_hi = p->row_hi;
     if (row_lo == 0 && row_hi == 0) row_hi = N;
     if (row_lo < 0 || row_hi > N || row_lo >= row_hi) return fail(FLOCK_EINVAL, "bad row range [%d,%d)", row_lo, row_hi);
+    if ((p->flags & FLOCK_EXACT_ORDER) && tbytes != 8) return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER is an f64 mode");
+    if ((p->flags & FLOCK_KNN_OBS) && p->knn != flock::KNN_K)
+        return fail(FLOCK_EUNSUPPORTED, "knn=%d: only %d is built", p->knn, flock::KNN_K);
+    if (!(p->action_scalar != 0.0)) return fail(FLOCK_EINVAL, "action_scalar must be non-zero");
+    return FLOCK_OK;
+}
+
+// ---- group kernel: G whole envs per CTA, one thread per row --------------------------------------------------------------
+// Cost model for G: the step is issue bound, so an SM's time is proportional to the threads it hosts per wave; minimise
+// (full waves) * occ * T + ceil(rest / 148) * T over the G that fit, preferring fuller CTAs on ties.
+bool group_layout(const FlockParams *p, int tbytes, bool knn, int G, flock::GArgs &g, int &threads, size_t &smem) {
+    const int N = p->n_agents;
+    const bool pa32 = (tbytes == 4);
+    const int NP2 = (N + 1) / 2;
+    const int W = pa32 ? (2 * NP2 + 31) / 32 : (N + 31) / 32;
+    threads = round_up32(G * N);
+    if (threads > flock::GMAXT) return false;
+    g.xs_bytes = align16((size_t)G * N * 32);
+    g.pf_bytes = pa32 ? align16((size_t)G * NP2 * 16) : 0;
+    g.stats_bytes = align16((size_t)G * flock::STATS_PER_ENV * 8);
+    g.off_xs = 0;
+    g.off_pf = g.off_xs + 2 * g.xs_bytes;
+    g.off_masks = g.off_pf + 2 * g.pf_bytes;
+    g.off_stats = align16((size_t)g.off_masks + (size_t)flock::GMS * (W + 1) * 4);     // one spare word row (prefetch)
+    g.off_idg = g.off_stats + 2 * g.stats_bytes;
+    g.off_obs = align16((size_t)g.off_idg + (size_t)threads * 8);
+    smem = (size_t)g.off_obs + (knn ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0);
+    g.G = G; g.NP2 = NP2; g.W = W;
+    return smem <= kMaxSmem;
+}
+
+bool plan_group(const FlockParams *p, int tbytes, bool knn, Plan &pl) {
+    const int E = p->n_envs, N = p->n_agents;
+    if (N > flock::GMAXT) return false;
+    flock::GArgs &g = pl.g;
+    memset(&g, 0, sizeof(g));
+    int bestG = 0;
+    double best = 0.0;
+    const int forced = tune_group(p);
+    for (int G = 1; G <= std::min(E, flock::GMAXT / N); ++G) {
+        if (forced && G != std::min(forced, std::min(E, flock::GMAXT / N))) continue;
+        int T; size_t smem;
+        flock::GArgs tmp;
+        memset(&tmp, 0, sizeof(tmp));
+        if (!group_layout(p, tbytes, knn, G, tmp, T, smem)) continue;
+        const int occ = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(65536 / (64 * T), (228 * 1024) / (smem + 1024)), 2048 / T));
+        const long long ncta = (E + G - 1) / G;
+        const long long per_wave = (long long)kSMs * occ;
+        const long long full = ncta / per_wave, rest = ncta - full * per_wave;
+        const double total = ((double)full * occ + (double)((rest + kSMs - 1) / kSMs)) * T;
+        if (bestG == 0 || total < best * 0.999 || (total < best * 1.001 && G > bestG)) { best = total; bestG = G; }
+    }
+    if (bestG == 0) return false;
+    int T; size_t smem;
+    group_layout(p, tbytes, knn, bestG, g, T, smem);
+    g.E = E; g.N = N; g.steps = 1;
+    g.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
+    const double R = p->comm_radius, R2 = p->comm_radius2;
+    g.R2 = R2; g.Rm = (g.centralized || R2 > R) ? R : std::nextafter(R2, -1.0);
+    g.thrC = std::max(R, R2);
+    // conservative fp32 filter threshold (flock_env_kernel.cuh, phase A): tc (1 + 3e-6) + 16 rc (max|p| + 2 rc) 2^-24
+    const float tc = (float)g.thrC, rc = sqrtf(tc);
+    g.thr_a = tc * (1.0f + 3e-6f); g.thr_b = 16.0f * rc * 5.9604645e-8f; g.thr_c = 2.0f * rc;
+    g.inv_n = 1.0f / (float)N;
+    g.dt = p->dt; g.inv_ascale = 1.0 / p->action_scalar; g.var = step_variant(p);
+    g.ulim = 10.0 * g.inv_ascale;
+    if (p->u_clip > 0.0) g.ulim = std::min(g.ulim, p->u_clip);
+    pl.group = true; pl.lanes = 1; pl.threads = T; pl.grid = (E + bestG - 1) / bestG; pl.smem = smem;
+    return true;
+}
+
+// Decide the kernel, lanes-per-row, envs-per-CTA (or rows-per-tile) and the shared-memory layout.
+int make_plan(const FlockParams *p, int tbytes, Plan &pl, bool need_bits = false) {
+    int row_lo, row_hi;
+    int rc = validate(p, tbytes, row_lo, row_hi);
+    if (rc) return rc;
+    const int E = p->n_envs, N = p->n_agents;
     const int nrows = row_hi - row_lo;
+    pl.group = false;
     pl.exact = (p->flags & FLOCK_EXACT_ORDER) != 0;
     pl.knn = (p->flags & FLOCK_KNN_OBS) != 0;
-    if (pl.exact && tbytes != 8) return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER is an f64 mode");
-    if (pl.knn && p->knn != flock::KNN_K) return fail(FLOCK_EUNSUPPORTED, "knn=%d: only %d is built", p->knn, flock::KNN_K);
 
-    int lanes = p->lanes;
+    int lanes = need_bits ? 1 : p->lanes;
     if (pl.exact) {
         if (lanes > 1) return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER needs lanes = 1 (sequential j)");
         lanes = 1;
     } else if (lanes <= 0) {
         lanes = 1;
         const long long rows = (long long)E * nrows;
-        // one thread per row (in-warp row expansion, every output byte written once) as soon as every SM gets a CTA;
-        // several lanes per row only for small batches, where the step is latency bound (measured: 2048 x 50 runs
-        // 12.4 us with one lane, 23.9 us with two)
+        // one thread per row as soon as every SM gets a CTA; several lanes per row only for small batches, where the step
+        // is latency bound (measured: 2048 x 50 runs 12.4 us with one lane, 23.9 us with two)
         while (rows * lanes < (long long)kSMs * 256 && lanes < 32 && lanes * 2 <= N) lanes *= 2;
     } else if (lanes > 32 || (lanes & (lanes - 1))) {
         return fail(FLOCK_EINVAL, "lanes=%d must be a power of two <= 32", lanes);
     }
 
+    // whole envs per CTA (flock_group_kernel): fast modes, full rows, one thread per row, no obstacle variant
+    if (!pl.exact && lanes == 1 && nrows == N && p->n_obstacles == 0 && !tune_no_group(p) && plan_group(p, tbytes, pl.knn, pl))
+        return FLOCK_OK;
+
     // Rows per CTA window.  Small envs: flat windows over the E*nrows rows (every lane gets a row; a window stages
     // the few envs it touches).  Envs with at least a window of rows: row tiles per env.
     int threads = 256;
-    if ((p->reserved & 0xff) > 0) threads = std::min(256, 32 * (p->reserved & 0xff));     // tuning override
+    if (tune_threads(p) > 0) threads = std::min(256, 32 * tune_threads(p));
     int RT = std::max(1, threads / lanes);
     const long long rows_total = (long long)E * nrows;
     if (rows_total < RT) RT = (int)rows_total;
@@ -130,12 +217,13 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
         const double R = p->comm_radius, R2 = p->comm_radius2;
         k.Rm = (cen || R2 > R) ? R : std::nextafter(R2, -1.0);
     }
-    k.tune = p->reserved >> 8;
+    k.tune = tune_phases(p);
     // full rows, one thread per row: expand in the warp (coalesced stores, every byte written once);
-    // sharded rows / several lanes per row: bulk zero-fill + scatter
-    // (exact-order mode with long rows keeps the bulk fill: its long sequential compute phase hides the background fill)
-    k.out_mode = (lanes == 1 && nrows == N && !(pl.exact && (size_t)N * tbytes > 2048) && !((p->reserved >> 8) & 16)) ? 1 : 0;
-    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2; k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
+    // sharded rows / several lanes per row: zero-fill + scatter
+    // (exact-order mode with long rows keeps the up-front fill: its long sequential compute phase hides it)
+    k.out_mode = (lanes == 1 && nrows == N && !(pl.exact && (size_t)N * tbytes > 2048) && !(tune_phases(p) & 16)) ? 1 : 0;
+    k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2;
+    k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
     k.ulim = 10.0 * k.inv_ascale;
     if (p->u_clip > 0.0) k.ulim = std::min(k.ulim, p->u_clip);
     pl.lanes = lanes; pl.threads = threads;
@@ -143,65 +231,72 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl) {
     return FLOCK_OK;
 }
 
-template <typename T, int LANES, bool EXACT, bool KNN>
-int launch_one(const Plan &pl, cudaStream_t st) {
-    auto kern = flock::flock_env_kernel<T, LANES, EXACT, KNN>;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (configured_dev != dev) {   // opt in to > 48 KB dynamic shared memory once per (thread, device)
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        configured_dev = dev;
+inline bool misaligned(const void *p, uintptr_t a = 16) { return p && (reinterpret_cast<uintptr_t>(p) & (a - 1)); }
+
+flock::AuxOut aux_out(const FlockAux *aux, int N) {
+    flock::AuxOut o;
+    memset(&o, 0, sizeof(o));
+    o.WB = (N + 31) / 32;
+    if (aux) {
+        o.nonfinite = aux->nonfinite; o.adj_bits = aux->adj_bits; o.degree = aux->degree;
+        o.min_dist = aux->min_dist; o.vel_diff = aux->vel_diff;
     }
-    kern<<<pl.grid, pl.threads, pl.smem, st>>>(pl.k);
-    CUDA_TRY(cudaGetLastError());
+    return o;
+}
+
+int launch_plan(Plan &pl, int tbytes, cudaStream_t st, bool pdl) {
+    if (pl.group) return launch_group(pl.g, tbytes, pl.knn, pl.grid, pl.threads, pl.smem, st, pdl);
+    if (tbytes == 4) return launch_env_f32(pl.k, pl.lanes, pl.knn, pl.grid, pl.threads, pl.smem, st, pdl);
+    return launch_env_f64(pl.k, pl.lanes, pl.exact, pl.knn, pl.grid, pl.threads, pl.smem, st, pdl);
+}
+
+template <typename T>
+int check_step_args(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network, T *reward,
+                    double *u_next, T *obs, const FlockAux *aux, bool may_alias) {
+    if (!x_in) return fail(FLOCK_EINVAL, "x_in is NULL");
+    if (!may_alias && x_out && x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
+    if (!may_alias && u_in && u_next == u_in) return fail(FLOCK_EINVAL, "u_next must not alias u_in");
+    const bool sharded = !((p->row_lo == 0) && (p->row_hi == 0 || p->row_hi == p->n_agents));
+    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(u_next) || misaligned(obs) ||
+        misaligned(values, sharded ? std::min<uintptr_t>(16, 2 * sizeof(T)) : 16) || misaligned(network, sharded ? sizeof(T) : 16))
+        return fail(FLOCK_EALIGN, "device buffers must be 16-byte aligned (row-sharded calls: values 8 bytes, network element size)");
+    if (reward && (reinterpret_cast<uintptr_t>(reward) % sizeof(T)))
+        return fail(FLOCK_EALIGN, "reward must be aligned to its element size");
+    if (aux && (misaligned(aux->nonfinite, 4) || misaligned(aux->adj_bits, 4) || misaligned(aux->degree, 4) ||
+                misaligned(aux->min_dist, sizeof(T)) || misaligned(aux->vel_diff, sizeof(T))))
+        return fail(FLOCK_EALIGN, "FlockAux buffers must be element aligned");
     return FLOCK_OK;
 }
 
-template <typename T, bool KNN>
-int launch_lanes(const Plan &pl, cudaStream_t st) {
-    switch (pl.lanes) {
-        case 1: return launch_one<T, 1, false, KNN>(pl, st);
-        case 2: return launch_one<T, 2, false, KNN>(pl, st);
-        case 4: return launch_one<T, 4, false, KNN>(pl, st);
-        case 8: return launch_one<T, 8, false, KNN>(pl, st);
-        case 16: return launch_one<T, 16, false, KNN>(pl, st);
-        case 32: return launch_one<T, 32, false, KNN>(pl, st);
-    }
-    return fail(FLOCK_EINVAL, "lanes=%d", pl.lanes);
-}
-
-template <typename T>
-int launch(const Plan &pl, cudaStream_t st) {
-    if (pl.exact) {
-        if constexpr (std::is_same<T, double>::value)
-            return pl.knn ? launch_one<double, 1, true, true>(pl, st) : launch_one<double, 1, true, false>(pl, st);
-        else
-            return fail(FLOCK_EINVAL, "FLOCK_EXACT_ORDER is an f64 mode");
-    }
-    return pl.knn ? launch_lanes<T, true>(pl, st) : launch_lanes<T, false>(pl, st);
-}
-
-bool misaligned(const void *p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); }
-
+// One step, or (group kernel only) `steps` fused steps.  x_out / u_next receive the state / action after the last step.
 template <typename T>
 int step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
-              T *reward, double *u_next, T *obs, void *stream) {
+              T *reward, double *u_next, T *obs, const FlockAux *aux, void *stream, int steps = 1, T *rewards_all = nullptr,
+              bool *fused = nullptr) {
     Plan pl;
-    int rc = make_plan(p, (int)sizeof(T), pl);
+    int rc = make_plan(p, (int)sizeof(T), pl, aux && aux->adj_bits);
     if (rc) return rc;
-    if (!x_in) return fail(FLOCK_EINVAL, "x_in is NULL");
-    if (x_out && x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
-    if (u_in && u_next == u_in) return fail(FLOCK_EINVAL, "u_next must not alias u_in");
-    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values) || misaligned(network) ||
-        misaligned(u_next) || misaligned(obs))
-        return fail(FLOCK_EALIGN, "device buffers (except reward) must be 16-byte aligned");
-    if (reward && (reinterpret_cast<uintptr_t>(reward) % sizeof(T)))
-        return fail(FLOCK_EALIGN, "reward must be aligned to its element size");
+    if (fused) *fused = pl.group;
+    if (steps != 1 && !pl.group) return FLOCK_OK;          // the caller loops over single steps
+    // (the group kernel's CTAs own whole envs: each reads its inputs before it writes its outputs, so a fused rollout may
+    //  finish in the buffers it started from)
+    rc = check_step_args<T>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, aux, pl.group && steps != 1);
+    if (rc) return rc;
     if (pl.knn && !obs) pl.knn = false;
-    pl.k.x_in = x_in; pl.k.u_in = u_in; pl.k.x_out = x_out; pl.k.u_next = u_next;
-    pl.k.values = values; pl.k.network = network; pl.k.reward = reward; pl.k.obs = obs;
-    return launch<T>(pl, reinterpret_cast<cudaStream_t>(stream));
+    const flock::AuxOut ao = aux_out(aux, p->n_agents);
+    if (pl.group) {
+        flock::GArgs &g = pl.g;
+        g.x_in = x_in; g.u_in = u_in; g.x_out = x_out; g.u_out = u_next;
+        g.values = values; g.network = network; g.reward = reward; g.rewards_all = rewards_all; g.obs = obs;
+        g.aux = ao; g.steps = steps;
+    } else {
+        flock::KArgs &k = pl.k;
+        k.x_in = x_in; k.u_in = u_in; k.x_out = x_out; k.u_next = u_next;
+        k.values = values; k.network = network; k.reward = reward; k.obs = obs;
+        k.aux = ao;
+        if (ao.adj_bits && pl.lanes != 1) return fail(FLOCK_EINVAL, "FlockAux.adj_bits needs one thread per row");
+    }
+    return launch_plan(pl, (int)sizeof(T), reinterpret_cast<cudaStream_t>(stream), !tune_no_pdl(p));
 }
 
 template <typename T>
@@ -209,21 +304,27 @@ int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, doub
                  T *network, T *reward, T *rewards_all, T *obs, int32_t *final_in_b, void *stream) {
     if (steps < 0) return fail(FLOCK_EINVAL, "steps=%d", steps);
     if (!x_a || !x_b || !u_a || !u_b) return fail(FLOCK_EINVAL, "x_a/x_b/u_a/u_b must be non-NULL");
+    if (final_in_b) *final_in_b = (steps & 1);
+    if (steps == 0) return FLOCK_OK;
+    // small envs: ONE persistent launch runs all the steps (flock_group_kernel); the final state / action land where `steps`
+    // ping-pong launches would have left them
+    bool fused = false;
+    int rc = tune_no_fuse(p) ? FLOCK_OK : step_impl<T>(p, x_a, u_a, (steps & 1) ? x_b : x_a, values, network, reward, (steps & 1) ? u_b : u_a, obs, nullptr,
+                          stream, steps, rewards_all, &fused);
+    if (rc || fused) return rc;
     double *xi = x_a, *xo = x_b, *ui = u_a, *uo = u_b;
     for (int t = 0; t < steps; ++t) {
         T *r = rewards_all ? rewards_all + (size_t)t * p->n_envs : reward;
-        int rc = step_impl<T>(p, xi, ui, xo, values, network, r, uo, obs, stream);
+        rc = step_impl<T>(p, xi, ui, xo, values, network, r, uo, obs, nullptr, stream);
         if (rc) return rc;
         std::swap(xi, xo);
         std::swap(ui, uo);
     }
-    if (rewards_all && reward && steps > 0)
+    if (rewards_all && reward)
         CUDA_TRY(cudaMemcpyAsync(reward, rewards_all + (size_t)(steps - 1) * p->n_envs, sizeof(T) * p->n_envs,
                                  cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
-    if (final_in_b) *final_in_b = (steps & 1);
     return FLOCK_OK;
 }
-
 
 // ---- large swarms: prep kernel + streaming row kernel (flock_swarm_kernel.cuh) --------------------------------------
 struct SwarmLayout { size_t off_pf, off_partials, off_totals, off_counters, off_needy, bytes; int NP2, PB; };
@@ -242,23 +343,6 @@ SwarmLayout swarm_layout(int E, int N) {
     return L;
 }
 
-template <typename TO, int LANES>
-int swarm_launch(const flock::SArgs &a, bool knn, dim3 grid, size_t smem, cudaStream_t st) {
-    auto k0 = flock::flock_swarm_kernel<TO, LANES, false>;
-    auto k1 = flock::flock_swarm_kernel<TO, LANES, true>;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        configured_dev = dev;
-    }
-    if (knn) k1<<<grid, 256, smem, st>>>(a); else k0<<<grid, 256, smem, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FLOCK_OK;
-}
-
 template <typename T>
 int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
                     T *reward, double *u_next, T *obs, void *scratch, size_t scratch_bytes, void *stream) {
@@ -274,9 +358,9 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     if (row_lo < 0 || row_hi > N || row_lo >= row_hi) return fail(FLOCK_EINVAL, "bad row range [%d,%d)", row_lo, row_hi);
     if (!x_in || !x_out || !scratch) return fail(FLOCK_EINVAL, "x_in, x_out and scratch are required");
     if (x_out == x_in) return fail(FLOCK_EINVAL, "x_out must not alias x_in");
-    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values) || misaligned(network) ||
-        misaligned(u_next) || misaligned(obs) || (reinterpret_cast<uintptr_t>(scratch) & 255u))
-        return fail(FLOCK_EALIGN, "device buffers must be 16-byte aligned (scratch: 256)");
+    if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values, std::min<uintptr_t>(16, 2 * sizeof(T))) ||
+        misaligned(network, sizeof(T)) || misaligned(u_next) || misaligned(obs) || (reinterpret_cast<uintptr_t>(scratch) & 255u))
+        return fail(FLOCK_EALIGN, "device buffers must be 16-byte aligned (values: 8, network: element size, scratch: 256)");
     const SwarmLayout L = swarm_layout(E, N);
     if (scratch_bytes < L.bytes) return fail(FLOCK_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, L.bytes);
     int lanes = p->lanes > 0 ? p->lanes : 32;
@@ -307,21 +391,9 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     const size_t smem = (size_t)a.off_bar + 16;
 
     CUDA_TRY(cudaMemsetAsync(a.counters, 0, (size_t)E * 8, st));
-    flock::flock_prep_kernel<<<dim3(L.PB, E), flock::PREP_THREADS, 0, st>>>(a, sizeof(T) == 4 ? 1 : 0);
-    CUDA_TRY(cudaGetLastError());
     const bool knn = a.obs != nullptr;
     const dim3 grid((row_hi - row_lo + a.RT - 1) / a.RT, E);
-    int rc;
-    switch (lanes) {
-        case 8: rc = swarm_launch<T, 8>(a, knn, grid, smem, st); break;
-        case 16: rc = swarm_launch<T, 16>(a, knn, grid, smem, st); break;
-        default: rc = swarm_launch<T, 32>(a, knn, grid, smem, st); break;
-    }
-    if (rc || !knn) return rc;
-    // rows whose kNN search found fewer than 7 agents inside the inflated radius: one CTA per row rescans everything
-    flock::flock_knn_fix_kernel<T><<<dim3(128, E), 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FLOCK_OK;
+    return launch_swarm(a, (int)sizeof(T), lanes, knn, L.PB, grid, smem, st);
 }
 
 }  // namespace
@@ -342,16 +414,7 @@ int reset_sample_impl(const FlockParams *p, double r_max, double v_max, double v
     flock::RArgs a;
     a.x_out = x_out; a.tries_out = tries_out; a.E = E; a.N = N; a.r_max = r_max; a.v_max = v_max; a.v_bias = v_bias;
     a.R2 = p->comm_radius2; a.min_dist = min_dist; a.seed = seed; a.max_tries = max_tries;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        CUDA_TRY(cudaFuncSetAttribute(flock::flock_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        configured_dev = dev;
-    }
-    flock::flock_reset_kernel<<<E, flock::RESET_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FLOCK_OK;
+    return launch_reset(a, smem, smem_cap, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- host-buffer context -------------------------------------------------------------------------------
@@ -362,6 +425,7 @@ struct FlockCtx {
     double *x[2];      // ping-pong state; x[cur] is the current state
     double *u[2];      // u[0]: action to apply (uploaded, or the cached controller action); u[1]: next
     void *values, *network, *reward, *obs;
+    void *stat_a, *stat_b;   // get_stats() scratch [E][N]
     int cur;
     int u_cached_flags;   // centralized flag the cached action was computed with; -1 = none
 };
@@ -375,15 +439,15 @@ size_t n_net(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * c
 size_t n_obs(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 4 * flock::KNN_K; }
 
 int ctx_run(FlockCtx *c, const double *u_dev, double *x_out, bool want_values, bool want_net, bool want_reward,
-            bool want_obs, double *u_next) {
+            bool want_obs, double *u_next, const FlockAux *aux = nullptr) {
     void *obs = (want_obs && (c->p.flags & FLOCK_KNN_OBS)) ? c->obs : nullptr;
     if (c->tbytes == 8)
         return step_impl<double>(&c->p, c->x[c->cur], u_dev, x_out, want_values ? (double *)c->values : nullptr,
                                  want_net ? (double *)c->network : nullptr, want_reward ? (double *)c->reward : nullptr,
-                                 u_next, (double *)obs, c->stream);
+                                 u_next, (double *)obs, aux, c->stream);
     return step_impl<float>(&c->p, c->x[c->cur], u_dev, x_out, want_values ? (float *)c->values : nullptr,
                             want_net ? (float *)c->network : nullptr, want_reward ? (float *)c->reward : nullptr, u_next,
-                            (float *)obs, c->stream);
+                            (float *)obs, aux, c->stream);
 }
 
 int ctx_fetch(FlockCtx *c, void *values_host, void *network_host, void *reward_host, void *obs_host) {
@@ -399,18 +463,49 @@ int ctx_fetch(FlockCtx *c, void *values_host, void *network_host, void *reward_h
 
 }  // namespace
 
+template <typename T>
+static int aggregate_impl(const FlockParams *p, const T *x, int32_t F, const T *prev, const uint32_t *adj_bits, int32_t L,
+                          int32_t pool, T *out, void *stream) {
+    if (!p || !x || !adj_bits || !out) return fail(FLOCK_EINVAL, "NULL argument");
+    if (p->n_envs < 1 || p->n_agents < 1 || F < 1 || L < 1) return fail(FLOCK_EINVAL, "bad sizes (E=%d N=%d F=%d L=%d)", p->n_envs, p->n_agents, F, L);
+    if (pool != FLOCK_POOL_MEAN && pool != FLOCK_POOL_SUM) return fail(FLOCK_EINVAL, "pool=%d", pool);
+    if ((const void *)out == (const void *)prev || (const void *)out == (const void *)x) return fail(FLOCK_EINVAL, "out must not alias prev or x");
+    flock::AggArgs a;
+    a.x = x; a.prev = prev; a.bits = adj_bits; a.out = out;
+    a.E = p->n_envs; a.N = p->n_agents; a.F = F; a.L = L; a.WB = (p->n_agents + 31) / 32; a.pool = pool;
+    return launch_aggregate(a, (int)sizeof(T), reinterpret_cast<cudaStream_t>(stream));
+}
+template <typename T>
+static int repulsion_impl(const FlockParams *p, const double *pos, int32_t stride, const T *weights, double cutoff_r2, T *out,
+                          void *stream) {
+    if (!p || !pos || !weights || !out) return fail(FLOCK_EINVAL, "NULL argument");
+    if (p->n_envs < 1 || p->n_agents < 1 || stride < 2) return fail(FLOCK_EINVAL, "bad sizes (E=%d N=%d stride=%d)", p->n_envs, p->n_agents, stride);
+    flock::ShepArgs a;
+    a.pos = pos; a.weights = weights; a.out = out; a.E = p->n_envs; a.N = p->n_agents; a.stride = stride; a.cutoff_r2 = cutoff_r2;
+    return launch_shepherd(a, (int)sizeof(T), reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" {
 
 int flock_abi_version(void) { return FLOCK_ABI_VERSION; }
 const char *flock_last_error(void) { return g_err.c_str(); }
+int flock_adj_words(int32_t n_agents) { return n_agents > 0 ? (n_agents + 31) / 32 : 0; }
 
 int flock_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
                    double *network, double *reward, double *u_next, double *obs, void *stream) {
-    return step_impl<double>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, stream);
+    return step_impl<double>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, nullptr, stream);
 }
 int flock_step_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, float *values,
                    float *network, float *reward, double *u_next, float *obs, void *stream) {
-    return step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, stream);
+    return step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, nullptr, stream);
+}
+int flock_step_aux_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
+                       double *network, double *reward, double *u_next, double *obs, const FlockAux *aux, void *stream) {
+    return step_impl<double>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, aux, stream);
+}
+int flock_step_aux_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, float *values,
+                       float *network, float *reward, double *u_next, float *obs, const FlockAux *aux, void *stream) {
+    return step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, aux, stream);
 }
 int flock_rollout_f64(const FlockParams *p, int32_t steps, double *x_a, double *x_b, double *u_a, double *u_b,
                       double *values, double *network, double *reward, double *rewards_all, double *obs,
@@ -441,6 +536,23 @@ int flock_swarm_step_f32(const FlockParams *p, const double *x_in, const double 
                          float *network, float *reward, double *u_next, float *obs, void *scratch, size_t scratch_bytes,
                          void *stream) {
     return swarm_step_impl<float>(p, x_in, u_in, x_out, values, network, reward, u_next, obs, scratch, scratch_bytes, stream);
+}
+
+int flock_aggregate_f64(const FlockParams *p, const double *x, int32_t F, const double *prev, const uint32_t *adj_bits,
+                        int32_t L, int32_t pool, double *out, void *stream) {
+    return aggregate_impl<double>(p, x, F, prev, adj_bits, L, pool, out, stream);
+}
+int flock_aggregate_f32(const FlockParams *p, const float *x, int32_t F, const float *prev, const uint32_t *adj_bits,
+                        int32_t L, int32_t pool, float *out, void *stream) {
+    return aggregate_impl<float>(p, x, F, prev, adj_bits, L, pool, out, stream);
+}
+int flock_repulsion_f64(const FlockParams *p, const double *pos, int32_t stride, const double *weights, double cutoff_r2,
+                        double *out, void *stream) {
+    return repulsion_impl<double>(p, pos, stride, weights, cutoff_r2, out, stream);
+}
+int flock_repulsion_f32(const FlockParams *p, const double *pos, int32_t stride, const float *weights, double cutoff_r2,
+                        float *out, void *stream) {
+    return repulsion_impl<float>(p, pos, stride, weights, cutoff_r2, out, stream);
 }
 
 void *flock_host_alloc(size_t bytes) {
@@ -492,6 +604,7 @@ void flock_ctx_destroy(FlockCtx *c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (int i = 0; i < 2; ++i) { cudaFree(c->x[i]); cudaFree(c->u[i]); }
     cudaFree(c->values); cudaFree(c->network); cudaFree(c->reward); cudaFree(c->obs);
+    cudaFree(c->stat_a); cudaFree(c->stat_b);
     cudaGetLastError();
     delete c;
 }
@@ -517,6 +630,14 @@ int flock_ctx_set_state(FlockCtx *c, const double *x_host, void *values_host, vo
     if (rc) return rc;
     c->u_cached_flags = c->p.flags & FLOCK_CENTRALIZED;
     return ctx_fetch(c, values_host, network_host, reward_host, obs_host);
+}
+
+int flock_ctx_upload_state(FlockCtx *c, const double *x_host) {
+    if (!c || !x_host) return fail(FLOCK_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->x[c->cur], x_host, n_x(c) * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FLOCK_OK;
 }
 
 int flock_ctx_step(FlockCtx *c, const double *u_host, void *values_host, void *network_host, void *reward_host,
@@ -558,6 +679,25 @@ int flock_ctx_get_state(FlockCtx *c, double *x_host) {
     if (!c || !x_host) return fail(FLOCK_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(x_host, c->x[c->cur], n_x(c) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FLOCK_OK;
+}
+
+int flock_ctx_get_stats(FlockCtx *c, void *vel_diffs_host, void *min_dists_host) {
+    if (!c) return fail(FLOCK_EINVAL, "NULL context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->p.n_envs * c->p.n_agents * c->tbytes;
+    if (!c->stat_a) CUDA_TRY(cudaMalloc(&c->stat_a, bytes));
+    if (!c->stat_b) CUDA_TRY(cudaMalloc(&c->stat_b, bytes));
+    FlockAux aux;
+    memset(&aux, 0, sizeof(aux));
+    aux.vel_diff = vel_diffs_host ? c->stat_a : nullptr;
+    aux.min_dist = min_dists_host ? c->stat_b : nullptr;
+    // a pair pass on the current state with no other output (the cached action is left alone: u_next = NULL)
+    int rc = ctx_run(c, nullptr, nullptr, false, false, false, false, nullptr, &aux);
+    if (rc) return rc;
+    if (vel_diffs_host) CUDA_TRY(cudaMemcpyAsync(vel_diffs_host, c->stat_a, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (min_dists_host) CUDA_TRY(cudaMemcpyAsync(min_dists_host, c->stat_b, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return FLOCK_OK;
 }

@@ -66,6 +66,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// programmatic dependent launch: every kernel waits here before its first global access, so a launch may be scheduled
+// while its predecessor in the stream drains (no-ops when the launch did not ask for it)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- exact-order Euler step, flocking_relative.py:96-105 ----------------------------------------
 // ((p + (v*dt)) + (((a*dt)*dt)*0.5)),  v + (a*dt),  a = u*action_scalar; every op rounded separately.
 __device__ __forceinline__ double4 integrate_exact(double4 x, double2 u, double dt, double ascale) {

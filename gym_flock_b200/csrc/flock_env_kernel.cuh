@@ -41,7 +41,17 @@
 
 namespace flock {
 
+struct AuxOut {               // optional extra outputs (FlockAux of the C ABI); all nullable
+    int *nonfinite;           // [E] set to 1 when a feature / action of the env is NaN or Inf
+    unsigned *adj_bits;       // [E][N][WB] exact adjacency bits: bit (j & 31) of word j >> 5 (one thread per row only)
+    int *degree;              // [E][N]
+    void *min_dist;           // [E][N] TO  get_stats()['min_dists']   flocking_relative.py:141-142
+    void *vel_diff;           // [E][N] TO  get_stats()['vel_diffs']   flocking_relative.py:138-140
+    int WB;                   // words per row: ceil(N / 32)
+};
+
 struct KArgs {
+    AuxOut aux;
     const double *x_in;
     const double *u_in;
     double *x_out;
@@ -89,7 +99,8 @@ __device__ __forceinline__ int bfind(const unsigned v) {        // index of the 
 __device__ __forceinline__ void smem_add(double *p, double v) { atomicAdd(p, v); }
 
 constexpr int STATS_PER_ENV = 4;   // sum vx, sum vy over the env (fp64), ready flag, pad
-constexpr int TOPK = KNN_K + 1;    // the diagonal (r2 = 0) rides along and is dropped at the end
+constexpr int TOPK = KNN_K + 2;    // the diagonal (r2 = 0) rides along, plus one slack slot: the fast modes select with
+                                   // approximate keys and re-rank the TOPK survivors with the reference's own keys
 
 template <typename T> struct TopK {
     T d[TOPK];
@@ -117,6 +128,46 @@ template <typename T> struct TopK {
         d[TOPK - 1] = Tr<T>::inf(); id[TOPK - 1] = self;
     }
 };
+
+// Final ranking of the kNN candidates with the REFERENCE's keys: r2 = dx*dx + dy*dy, every operation rounded separately
+// (flocking_relative.py:114), ties to the lower index.  `id` holds TOPK agent indices found with approximate keys (fp32 /
+// fused fp64); the row's own index (the diagonal, or an unused slot) sorts last.  The approximate order is almost always
+// right, so check first and run the insertion network only when some lane of the warp is out of order.
+__device__ __forceinline__ void knn_rerank(const double4 xi, const int i, const double4 *xe, int (&id)[TOPK]) {
+    double key[TOPK];
+#pragma unroll
+    for (int m = 0; m < TOPK; ++m) {
+        const double4 xj = xe[id[m]];
+        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+        key[m] = (id[m] == i) ? CUDART_INF : __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    }
+    bool sorted = true;
+#pragma unroll
+    for (int m = 0; m + 1 < TOPK; ++m)
+        sorted = sorted && (key[m] < key[m + 1] || (key[m] == key[m + 1] && id[m] <= id[m + 1]));
+    if (__any_sync(__activemask(), !sorted)) {
+#pragma unroll
+        for (int p = 1; p < TOPK; ++p) {
+#pragma unroll
+            for (int q = p; q > 0; --q) {
+                const bool sw = key[q] < key[q - 1] || (key[q] == key[q - 1] && id[q] < id[q - 1]);
+                const double ka = sw ? key[q] : key[q - 1], kb = sw ? key[q - 1] : key[q];
+                const int ia = sw ? id[q] : id[q - 1], ib = sw ? id[q - 1] : id[q];
+                key[q - 1] = ka; key[q] = kb; id[q - 1] = ia; id[q] = ib;
+            }
+        }
+    }
+}
+
+// 1/deg in the output type, shared by every kernel so that row shards, lanes and kernels agree bit for bit.
+__device__ __forceinline__ float inv_deg(const int deg, float) {
+    const float d = (float)max(deg, 1);
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    const float e = fmaf(-d, y, 1.0f);         // one Newton step on the MUFU seed
+    return fmaf(y, e, y);
+}
+__device__ __forceinline__ double inv_deg(const int deg, double) { return Tr<double>::rcp((double)max(deg, 1)); }
 
 struct Acc {
     double f0, f1, f2, f3, f4, f5;   // masked feature sums
@@ -359,7 +410,7 @@ __device__ __forceinline__ void stage_window(const KArgs &a, unsigned char *smem
     FLOCK_WIN_LOCALS
 
     // ---- stats flags ----------------------------------------------------------------------------------------------------
-    if constexpr (!EXACT) for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
+    for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
 
     // ---- prologue: load, integrate, publish x', stage (one flat loop over the agents of the staged envs) -----------
     {
@@ -423,16 +474,22 @@ __device__ __forceinline__ void window_stats(const KArgs &a, unsigned char *smem
             const bool owner = reward && (r0 <= env * nre) && (env * nre < r1);     // CTA holding the env's first row
             const double4 *xe = xs + ge * N;
             if constexpr (EXACT) {
-                if (lane == 0 && owner) {   // NumPy's two-pass variance with sequential sums (:145-147)
+                if (lane == 0 && (owner || a.aux.vel_diff != nullptr)) {   // NumPy's two-pass variance with sequential sums (:145-147)
                     double sx = 0.0, sy = 0.0;
                     for (int j = 0; j < N; ++j) { sx = __dadd_rn(sx, xe[j].z); sy = __dadd_rn(sy, xe[j].w); }
                     const double mx = __ddiv_rn(sx, (double)N), my = __ddiv_rn(sy, (double)N);
-                    double qx = 0.0, qy = 0.0;
-                    for (int j = 0; j < N; ++j) {
-                        const double ex = __dsub_rn(xe[j].z, mx), ey = __dsub_rn(xe[j].w, my);
-                        qx = __dadd_rn(qx, __dmul_rn(ex, ex)); qy = __dadd_rn(qy, __dmul_rn(ey, ey));
+                    if (owner) {
+                        double qx = 0.0, qy = 0.0;
+                        for (int j = 0; j < N; ++j) {
+                            const double ex = __dsub_rn(xe[j].z, mx), ey = __dsub_rn(xe[j].w, my);
+                            qx = __dadd_rn(qx, __dmul_rn(ex, ex)); qy = __dadd_rn(qy, __dmul_rn(ey, ey));
+                        }
+                        reward[env] = __dmul_rn(-1.0, __dadd_rn(__ddiv_rn(qx, (double)N), __ddiv_rn(qy, (double)N)));
                     }
-                    reward[env] = __dmul_rn(-1.0, __dadd_rn(__ddiv_rn(qx, (double)N), __ddiv_rn(qy, (double)N)));
+                    double *st = stats + ge * STATS_PER_ENV;      // np.mean(v, axis=0) for get_stats() (:138)
+                    st[0] = mx; st[1] = my;
+                    __threadfence_block();
+                    reinterpret_cast<volatile double *>(st)[2] = 1.0;
                 }
             } else {
                 // sums about agent 0's velocity (a member of the flock: no cancellation problem)
@@ -672,6 +729,7 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                 nb[m] = top.id[m];
             }
         }
+        if constexpr (!EXACT) knn_rerank(xi, i, xe, nb);     // exact order / membership among the TOPK survivors
         // One thread per row and full rows: the warp's 32 observation rows are contiguous in memory (32 x 28 values).  A
         // lane writing its own row directly issues 28 scalar stores 112 bytes apart from its neighbours' -- partial sectors
         // that made Flocking-v0 4x slower than FlockingRelative-v0; stage the block in shared memory and copy it out with
@@ -799,8 +857,7 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
     // ---- row epilogue: features, action, 1/deg ---------------------------------------------------------------
     TO idg;
     if constexpr (EXACT) idg = __ddiv_rn(1.0, (double)max(deg, 1));               // :121-122
-    else if constexpr (PA32) idg = __frcp_rn((float)max(deg, 1));
-    else idg = Tr<double>::rcp((double)max(deg, 1));
+    else idg = inv_deg(deg, TO(0));
     if (valid && sub == 0) {
         if (a.values) {
             TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
@@ -846,6 +903,69 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
                 }
             }
             reinterpret_cast<double2 *>(a.u_next)[grow] = make_double2(ux, uy);
+        }
+    }
+
+    // ---- optional outputs (FlockAux): non-finite guard, degree, exact adjacency bits, get_stats() -------------------------
+    if (a.aux.nonfinite != nullptr || a.aux.degree != nullptr || a.aux.adj_bits != nullptr || a.aux.min_dist != nullptr ||
+        a.aux.vel_diff != nullptr) {
+        if (a.aux.nonfinite != nullptr && valid && sub == 0) {
+            const double chk = ((A.f0 + A.f1) + (A.f2 + A.f3)) + ((A.f4 + A.f5) + (A.gx + A.gy)) + ((xi.x + xi.y) + (xi.z + xi.w));
+            if (!(fabs(chk) < CUDART_INF)) a.aux.nonfinite[env] = 1;
+        }
+        if (a.aux.degree != nullptr && valid && sub == 0) a.aux.degree[grow] = deg;
+        if constexpr (LANES == 1) {
+            if (a.aux.adj_bits != nullptr && valid)
+                for (int w = 0; w < a.aux.WB; ++w) a.aux.adj_bits[grow * a.aux.WB + w] = (w < nw) ? mrow[w * MS] : 0u;
+        }
+        if (a.aux.min_dist != nullptr) {
+            // min_j sqrt(r2) (flocking_relative.py:141-142; r2 is symmetric, so the column minimum is the row minimum).  Every
+            // neighbour is closer than every non-neighbour: scan the exact adjacency bits; a row without neighbours scans all.
+            auto r2_of = [&](const int j) -> double {
+                const double4 xj = xe[j];
+                if constexpr (EXACT) {
+                    const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+                    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                } else {
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    return fma(dx, dx, dy * dy);
+                }
+            };
+            double m2 = CUDART_INF;
+            if (valid) {
+                for (int w = 0; w < nw; ++w) {
+                    unsigned b = mrow[w * MS];
+                    while (b) { const int k = __ffs(b) - 1; b &= b - 1; m2 = fmin(m2, r2_of(j_of(w * 32 + k))); }
+                }
+            }
+            if constexpr (LANES > 1) {
+#pragma unroll
+                for (int m = LANES / 2; m > 0; m >>= 1) m2 = fmin(m2, shfl_xor(m2, m));
+            }
+            if (__any_sync(0xffffffffu, valid && deg == 0)) {
+                if (valid && deg == 0) for (int j = sub; j < N; j += LANES) if (j != i) m2 = fmin(m2, r2_of(j));
+                if constexpr (LANES > 1) {
+#pragma unroll
+                    for (int m = LANES / 2; m > 0; m >>= 1) m2 = fmin(m2, shfl_xor(m2, m));
+                }
+            }
+            if (valid && sub == 0) {
+                if constexpr (EXACT) reinterpret_cast<TO *>(a.aux.min_dist)[grow] = __dsqrt_rn(m2);
+                else reinterpret_cast<TO *>(a.aux.min_dist)[grow] = (TO)sqrt(m2);
+            }
+        }
+        if (a.aux.vel_diff != nullptr && valid && sub == 0) {
+            const volatile double *st = stats + g * STATS_PER_ENV;
+            while (st[2] == 0.0) { }
+            __threadfence_block();
+            if constexpr (EXACT) {                        // sqrt(sum((v - mean)^2, axis=1)) (:138-140), NumPy's rounding
+                const double ex = __dsub_rn(xi.z, st[0]), ey = __dsub_rn(xi.w, st[1]);
+                reinterpret_cast<TO *>(a.aux.vel_diff)[grow] = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+            } else {
+                const double invN = 1.0 / (double)N;
+                const double ex = xi.z - st[0] * invN, ey = xi.w - st[1] * invN;
+                reinterpret_cast<TO *>(a.aux.vel_diff)[grow] = (TO)sqrt(fma(ex, ex, ey * ey));
+            }
         }
     }
 
@@ -903,6 +1023,7 @@ __global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_
     unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);
     TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
     const Win win = window_of(a, blockIdx.x);
+    pdl_wait();
     stage_window<TO, EXACT>(a, smem, win);
     __syncthreads();
     window_stats<TO, EXACT>(a, smem, win);

@@ -1,0 +1,533 @@
+// flock_group_kernel.cuh -- the batched flocking step for small environments (N <= 512), sm_100a.
+//
+// Same algorithm and the same per-row arithmetic as flock_env_kernel.cuh ("filter then refine", one thread per row),
+// restructured around WHOLE environments:
+//
+//   * A CTA owns G complete envs (G*N rows, one thread per row; G is chosen so that G*N fills the CTA: 5 envs of 100
+//     agents in 512 threads).  Nothing is staged twice, no window crosses an env, every index is a compile-time
+//     expression when N is a template constant (NC = 100 / 50; NC = 0: run-time N).
+//   * The kernel runs `steps` consecutive steps of the driver loop {u = controller(); step(u)} without
+//     leaving the SM: the state lives in shared memory (two copies, by step parity), the row owner integrates its own
+//     agent with the action it has just computed and publishes it for the next step, so ONE block barrier separates two
+//     steps.  Envs never interact, so no CTA ever waits for another: flock_rollout_* is one launch, and the tail of the
+//     grid is paid once per rollout instead of once per step.  Every step still writes all of its outputs (values, the
+//     dense adjacency, reward, obs) -- the stores of step t drain while step t+1 filters.
+//   * steps = 1 is the per-step API (flock_step_*): state and action come from global memory, x_out / u_next go back.
+//
+//   per step and row i (flocking_relative.py):
+//     stats     reward = -(var vx + var vy), sum_j v_j (alignment identity)                     :145-147, :204-208
+//     filter    all N pairs, packed f32x2 sign test on positions relative to the env origin      :113-117
+//     refine    the ~deg candidates in fp64: exact adjacency bit, 6 feature sums, gradient       :117-129, :214-226
+//     epilogue  values, u = clip(.)/10, next state = integrate(x_i, u)                           :96-105, :209-211
+//     rows      the warp's 32 rows of adj_mean from the exact bit masks, 16-byte streaming stores :120-122
+//     kNN       Flocking-v0: 7 nearest by r2, re-ranked with the reference's own keys              flocking.py:20-24
+#pragma once
+#include "flock_env_kernel.cuh"
+
+namespace flock {
+
+struct GArgs {
+    const double *x_in;       // [E][N][4] state before the first step
+    const double *u_in;       // [E][N][2] action of the first step (NULL: no integration in the first step)
+    double *x_out;            // state after the last step (nullable)
+    double *u_out;            // controller() on the state after the last step (nullable)
+    void *values, *network, *reward, *rewards_all, *obs;
+    AuxOut aux;
+    int E, N, G, steps;
+    int NP2;                  // pair slots per env in the packed fp32 position array
+    int W;                    // 32-bit candidate words per row
+    int centralized;
+    float thr_a, thr_b, thr_c;   // per-row filter threshold: thr_a + thr_b * (max(|px|, |py|) + thr_c)
+    float inv_n;
+    double thrC, R2, Rm, dt, inv_ascale, ulim;
+    StepVariant var;
+    unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
+    unsigned xs_bytes, pf_bytes, stats_bytes;    // size of ONE copy of the parity-duplicated arrays
+};
+
+constexpr int GMS = 512;      // mask words are word-major with this fixed stride (immediate offsets everywhere)
+constexpr int GMAXT = 512;
+
+// ---- in-warp expansion of 32 consecutive rows of adj_mean, N a compile-time constant ---------------------------------
+// Row r of the warp lives N elements after row r-1: with N known every store address is dst + immediate, the mask word
+// and 1/deg loads use immediate offsets too, so a row costs two LDS, the bit -> value selects and one 16-byte store.
+template <typename TO, int NC, int STRIDE>
+__device__ __forceinline__ void expand_rows_const(TO *wout, const unsigned *wm, const TO *idgs, const int nrows, const int lane) {
+    constexpr int VMAX = 16 / (int)sizeof(TO);
+    constexpr int V = (NC % VMAX == 0) ? VMAX : ((VMAX == 4 && NC % 2 == 0) ? 2 : ((VMAX == 2 && NC % 2 == 0) ? 2 : 1));
+    constexpr int nv = NC / V;                          // groups per row
+    if constexpr (nv <= 32) {
+        constexpr int rpi = 32 / nv;                    // rows per iteration
+        const int sr = lane / nv;                       // this lane's sub-row within an iteration
+        const int cv = lane - sr * nv;
+        const bool on = sr < rpi;
+        const int c = on ? cv * V : 0;
+        const int sh = c & 31;
+        const unsigned *mp = wm + (c >> 5) * STRIDE + (on ? sr : 0);
+        const TO *ip = idgs + (on ? sr : 0);
+        TO *dst = wout + (on ? sr : 0) * NC + c;
+        const int last = nrows - sr;                    // this lane stores while r < last
+        if (nrows == 32) {
+#pragma unroll
+            for (int r = 0; r < 32; r += rpi) {
+                const bool go = on && (rpi == 1 || r < last);
+                store_group<TO, V>(dst + r * NC, mp[r] >> sh, ip[r], go);
+            }
+        } else {
+            for (int r = 0; r < nrows; r += rpi) {
+                const bool go = on && r < last;
+                store_group<TO, V>(dst + r * NC, go ? (mp[r] >> sh) : 0u, go ? ip[r] : TO(0), go);
+            }
+        }
+    } else {
+        const int sh = (lane * V) & 31;
+        const unsigned *mp0 = wm + ((lane * V) >> 5) * STRIDE;
+        for (int r = 0; r < nrows; ++r) {
+            const TO v = idgs[r];
+            const unsigned *mp = mp0 + r;
+            TO *dst = wout + (size_t)r * NC + lane * V;
+#pragma unroll 4
+            for (int cv = lane; cv < nv; cv += 32) {
+                store_group<TO, V>(dst, *mp >> sh, v, true);
+                mp += V * STRIDE; dst += 32 * V;
+            }
+        }
+    }
+}
+
+// generic N: flock_env_kernel's expand_rows with this kernel's mask stride
+template <typename TO, int V>
+__device__ __forceinline__ void expand_rows_g(TO *wout, const unsigned *wm, const TO *idgs, const int N, const int nrows,
+                                              const int lane) {
+    const int nv = N / V;
+    const int passes = (nv + 31) >> 5;
+    const int rpi = (nv >= 32) ? 1 : 32 / nv;
+    const int sr = (nv >= 32) ? 0 : lane / nv;
+    const int cv0 = (nv >= 32) ? lane : lane - sr * nv;
+    const bool lane_on = (nv >= 32) || (sr < rpi);
+    if (passes == 1) {
+        const bool on = lane_on && cv0 < nv;
+        const int c = on ? cv0 * V : 0;
+        const int sh = c & 31;
+        const unsigned *mp = wm + (c >> 5) * GMS + (on ? sr : 0);
+        const TO *ip = idgs + (on ? sr : 0);
+        TO *dst = wout + (size_t)(on ? sr : 0) * N + c;
+        const size_t dstep = (size_t)rpi * N;
+        const int last = nrows - sr;
+        for (int r = 0; r < nrows; r += rpi) {
+            const bool go = on && r < last;
+            store_group<TO, V>(dst, go ? (mp[r] >> sh) : 0u, go ? ip[r] : TO(0), go);
+            dst += dstep;
+        }
+    } else {
+        const int sh = (lane * V) & 31;
+        const unsigned *mp0 = wm + ((lane * V) >> 5) * GMS;
+        for (int r = 0; r < nrows; ++r) {
+            const TO v = idgs[r];
+            const unsigned *mp = mp0 + r;
+            TO *dst = wout + (size_t)r * N + lane * V;
+#pragma unroll 4
+            for (int cv = lane; cv < nv; cv += 32) {
+                store_group<TO, V>(dst, *mp >> sh, v, true);
+                mp += V * GMS; dst += 32 * V;
+            }
+        }
+    }
+}
+
+template <typename TO, bool KNN, int NC>
+__global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
+    constexpr bool PA32 = std::is_same<TO, float>::value;
+    using TK = typename std::conditional<PA32, float, double>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = NC ? NC : a.N;
+    const int NP2 = NC ? (NC + 1) / 2 : a.NP2;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int e0 = blockIdx.x * a.G;
+    const int genv = min(a.G, a.E - e0);
+    const int nrows = genv * N;                            // rows (agents) of this CTA
+    const bool valid = tid < nrows;
+    const int r = valid ? tid : 0;                         // idle threads shadow row 0 and store nothing
+    int g;
+    if constexpr (NC != 0) g = r / NC;
+    else g = (int)(((float)r + 0.5f) * a.inv_n);           // exact: r < 2^20
+    const int i = r - g * N;
+    const int env = e0 + g;
+    const size_t grow = (size_t)e0 * N + r;                // global row (agent) index
+    const bool cen = a.centralized != 0;
+    const int steps = a.steps;
+    unsigned *mrow = reinterpret_cast<unsigned *>(smem + a.off_masks) + tid;     // word w of this thread at mrow[w * GMS]
+    TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
+    TO *net = reinterpret_cast<TO *>(a.network);
+    const double R2r = a.R2, Rmr = a.Rm;
+
+    // ---- step-0 staging: state and action from global memory ---------------------------------------------------------------
+    for (int q = tid; q < 2 * genv; q += blockDim.x)       // ready counters of both parities
+        reinterpret_cast<double *>(smem + a.off_stats + (q >= genv ? a.stats_bytes : 0u))[(q % genv) * STATS_PER_ENV + 2] = 0.0;
+    pdl_wait();                                            // (programmatic dependent launch: the previous step's stores are visible)
+    if (valid) {
+        double4 x = ld_state(a.x_in + grow * 4);
+        const double2 ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (size_t)env * N * 4));   // env origin: agent 0 before the step
+        if (a.u_in) {
+            const double2 u = __ldg(reinterpret_cast<const double2 *>(a.u_in) + grow);
+            const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
+            x = plain ? integrate_exact(x, u, a.dt, a.var.step_scale) : integrate_variant(x, u, i, a.dt, a.var);
+        }
+        reinterpret_cast<double4 *>(smem + a.off_xs)[r] = x;
+        if constexpr (PA32) {
+            float *p = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem + a.off_pf) + g * NP2 + (i >> 1));
+            p[i & 1] = (float)(x.x - ref.x); p[2 + (i & 1)] = (float)(x.y - ref.y);
+            if ((N & 1) && i == N - 1) { p[1] = CUDART_INF_F; p[3] = CUDART_INF_F; }     // odd N: pad slot at infinity
+        }
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+        const unsigned par = (unsigned)(t & 1);
+        const bool last_step = (t == steps - 1);
+        const double4 *xs = reinterpret_cast<const double4 *>(smem + a.off_xs + par * a.xs_bytes);
+        const float4 *pf = reinterpret_cast<const float4 *>(smem + a.off_pf + par * a.pf_bytes);
+        double *stats = reinterpret_cast<double *>(smem + a.off_stats + par * a.stats_bytes);
+        __syncthreads();                                   // the state of step t is complete; everybody left step t-1
+
+        // ---- per-env velocity sums and reward: one warp per env, published through a step counter -----------------------
+        {
+            const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+            for (int ge = warp; ge < genv; ge += nwarps) {
+                const double4 *xe = xs + ge * N;
+                const double rx = xe[0].z, ry = xe[0].w;    // sums about agent 0's velocity (a member of the flock)
+                double sx = 0, sy = 0, qx = 0, qy = 0;
+                for (int j = lane; j < N; j += 32) {
+                    const double ex = xe[j].z - rx, ey = xe[j].w - ry;
+                    sx += ex; sy += ey; qx = fma(ex, ex, qx); qy = fma(ey, ey, qy);
+                }
+                sx = warp_sum(sx); sy = warp_sum(sy);
+                const double q = warp_sum(qx + qy);
+                if (lane == 0) {
+                    const double invN = 1.0 / (double)N;
+                    const TO rew = (TO)(-(q - (sx * sx + sy * sy) * invN) * invN);          // -(var vx + var vy)
+                    if (a.rewards_all) reinterpret_cast<TO *>(a.rewards_all)[(size_t)t * a.E + e0 + ge] = rew;
+                    if (a.reward && (last_step || !a.rewards_all)) reinterpret_cast<TO *>(a.reward)[e0 + ge] = rew;
+                    double *st = stats + ge * STATS_PER_ENV;
+                    st[0] = fma((double)N, rx, sx); st[1] = fma((double)N, ry, sy);          // sum_j v_j
+                    __threadfence_block();
+                    reinterpret_cast<volatile double *>(st)[2] = (double)(t + 1);            // ready
+                }
+            }
+        }
+
+        const double4 *xe = xs + g * N;
+        const double4 xi = xe[i];
+        if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
+
+        // ---- phase A: filter over all N pairs; candidate bits in shared memory, bit k of the row <-> agent k ------------------
+        int cnt = 0;
+        TopK<TK> top;
+        unsigned kp[TOPK];
+        unsigned kidx = 1;
+        constexpr bool KPACK = KNN && PA32;
+        if constexpr (KPACK) {
+            while ((int)kidx < N) kidx <<= 1;
+            kidx -= 1;
+#pragma unroll
+            for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;
+        } else if constexpr (KNN) {
+            top.init(i);
+        }
+        auto kp_insert = [&](unsigned k) {
+#pragma unroll
+            for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
+        };
+        int nw;
+        if constexpr (PA32) {
+            const int nslots = NP2;
+            nw = (2 * nslots + 31) >> 5;
+            const float4 *pe = pf + g * NP2;
+            const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
+            const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
+            const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
+            // conservative per-row threshold (covers the fp32 rounding of both positions and of the fused form)
+            const float thrA = fmaf(a.thr_b, fmaxf(fabsf(pxi), fabsf(pyi)) + a.thr_c, a.thr_a);
+            const float2 nthr2 = make_float2(-thrA, -thrA);
+            auto word = [&](const int w, const int tend, const bool full) {
+                unsigned bits = 0;
+                const int tbase = w * 16;
+                if constexpr (KNN) {
+                    auto body = [&](const int tt) {
+                        const float4 q = pe[tbase + tt];
+                        const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                        const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                        const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+                        bits |= (r2.x < thrA) ? (1u << (2 * tt)) : 0u;
+                        bits |= (r2.y < thrA) ? (2u << (2 * tt)) : 0u;
+                        const unsigned jw = (unsigned)(2 * tbase);
+                        kp_insert(((__float_as_uint(r2.x) & ~kidx) | jw) + (unsigned)(2 * tt));
+                        kp_insert(((__float_as_uint(r2.y) & ~kidx) | jw) + (unsigned)(2 * tt + 1));
+                    };
+                    if (full) {
+#pragma unroll
+                        for (int tt = 0; tt < 16; ++tt) body(tt);
+                    } else {
+                        for (int tt = 0; tt < tend; ++tt) body(tt);
+                    }
+                } else {
+                    // s = dx^2 + (dy^2 - thrA): the candidate test is the SIGN of s; one funnel shift per pair moves it into
+                    // the word (first pair ends up highest: one BREV per word)
+                    auto body = [&](const int tt) {
+                        const float4 q = pe[tbase + tt];
+                        const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                        const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                        const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
+                        bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
+                        bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+                    };
+                    if (full) {
+#pragma unroll
+                        for (int tt = 0; tt < 16; ++tt) body(tt);
+                        bits = __brev(bits);
+                    } else {
+                        for (int tt = 0; tt < tend; ++tt) body(tt);
+                        bits = __brev(bits) >> (32 - 2 * tend);      // 0 < tend < 16
+                    }
+                }
+                mrow[w * GMS] = bits;
+                cnt += __popc(bits);
+            };
+            if constexpr (NC != 0) {
+                constexpr int NS = (NC + 1) / 2, FW = NS / 16, TAIL = NS - FW * 16;
+#pragma unroll
+                for (int w = 0; w < FW; ++w) word(w, 16, true);
+                if constexpr (TAIL > 0) {
+                    unsigned bits = 0;
+                    if constexpr (!KNN) {
+#pragma unroll
+                        for (int tt = 0; tt < TAIL; ++tt) {
+                            const float4 q = pe[FW * 16 + tt];
+                            const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                            const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                            const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
+                            bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
+                            bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+                        }
+                        bits = __brev(bits) >> (32 - 2 * TAIL);
+                        mrow[FW * GMS] = bits;
+                        cnt += __popc(bits);
+                    } else {
+                        word(FW, TAIL, false);
+                    }
+                }
+            } else {
+                for (int w = 0; w * 16 < nslots; ++w) {
+                    const int tend = min(16, nslots - w * 16);
+                    word(w, tend, tend == 16);
+                }
+            }
+        } else {
+            nw = (N + 31) >> 5;
+            const double thrC = a.thrC;
+            for (int w = 0; w * 32 < N; ++w) {
+                unsigned bits = 0;
+                const int kbase = w * 32;
+                const int kend = min(32, N - kbase);
+                auto body = [&](const int kk) {
+                    const int j = kbase + kk;
+                    const double4 xj = xe[j];
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    const double r2 = fma(dx, dx, dy * dy);
+                    bits |= (r2 <= thrC) ? (1u << kk) : 0u;
+                    if constexpr (KNN) top.insert(r2, j);
+                };
+                if (kend == 32) {
+#pragma unroll 8
+                    for (int kk = 0; kk < 32; ++kk) body(kk);
+                } else {
+                    for (int kk = 0; kk < kend; ++kk) body(kk);
+                }
+                mrow[w * GMS] = bits;
+                cnt += __popc(bits);
+            }
+        }
+
+        // ---- kNN observation: obs[i, 4m:4m+4] = x_i - x_nbr(m), staged per warp and stored coalesced      flocking.py:20-24
+        if constexpr (KNN) {
+            int nb[TOPK];
+#pragma unroll
+            for (int m = 0; m < TOPK; ++m) {
+                if constexpr (KPACK) {
+                    const int id = (int)(kp[m] & kidx);
+                    nb[m] = (id < N) ? id : i;               // (odd N: the pad slot at +inf is not an agent)
+                } else {
+                    nb[m] = top.id[m];
+                }
+            }
+            knn_rerank(xi, i, xe, nb);
+            if (a.obs) {
+                TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
+                TO *o = obs_w + lane * (NXS * KNN_K);
+#pragma unroll
+                for (int m = 0; m < KNN_K; ++m) {            // the diagonal and unused slots sort last: a zero block (N <= 7)
+                    const double4 xn = xe[nb[m]];
+                    o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                    o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+                }
+                __syncwarp();
+                const int wr0 = tid - lane;                  // first row of this warp within the CTA
+                const int nrw = min(32, nrows - wr0);
+                if (nrw > 0) {
+                    const int nvec = nrw * (NXS * KNN_K) * (int)sizeof(TO) / 16;
+                    const float4 *src = reinterpret_cast<const float4 *>(obs_w);
+                    float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<TO *>(a.obs) + ((size_t)e0 * N + wr0) * (NXS * KNN_K));
+                    for (int v = lane; v < nvec; v += 32) __stcs(dst + v, src[v]);
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- phase B: refine the candidates in fp64, ascending j; the words end up holding the exact adjacency bits -------
+        Acc A;
+        A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
+        int deg = 0;
+        {
+            // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
+            mrow[(i >> 5) * GMS] &= ~(1u << (i & 31));
+            --cnt;
+            const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe);
+            unsigned waddr = (unsigned)__cvta_generic_to_shared(mrow);
+            const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 32u : 0u);
+            unsigned cand = mrow[0], nxt = mrow[GMS];         // (the mask region has one spare word row)
+            int jb = 0;
+            int left = valid ? cnt : 0;
+            while (left > 0) {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "setp.eq.u32 p, %0, 0;\n\t"
+                             "@p mov.u32 %0, %1;\n\t"
+                             "@p add.u32 %2, %2, %4;\n\t"
+                             "@p add.s32 %3, %3, 32;\n\t"
+                             "@p ld.shared.u32 %1, [%2+%4];\n\t}"
+                             : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(jb) : "n"(GMS * 4) : "memory");
+                const unsigned low = cand & (0u - cand);
+                cand ^= low;
+                const int j = jb + bfind(low);
+                const unsigned xaddr = low ? xe_s + (unsigned)j * 32u : xdummy;
+                refine_fast_pred<PA32>(xi, xaddr, low, waddr, R2r, Rmr, A, deg, left);
+            }
+        }
+        __syncwarp();
+
+        // ---- row epilogue: features, action, next state ----------------------------------------------------------------------
+        const TO idg = inv_deg(deg, TO(0));
+        idg_s[tid] = idg;
+        double ux, uy;
+        {
+            double sdx = A.f0, sdy = A.f3;                   // decentralized: the masked sums (:205-206)
+            if (cen) {                                       // centralized: sum_j (v_i - v_j) = N*v_i - sum_j v_j, about agent 0
+                const volatile double *st = stats + g * STATS_PER_ENV;
+                const double want = (double)(t + 1);
+                while (st[2] < want) { }                     // published right after the barrier by the stats warp
+                __threadfence_block();
+                const double rx = xe[0].z, ry = xe[0].w;
+                sdx = fma((double)N, xi.z - rx, -(st[0] - (double)N * rx));
+                sdy = fma((double)N, xi.w - ry, -(st[1] - (double)N * ry));
+            }
+            const double ia = a.inv_ascale, ul = a.ulim;
+            const double rawx = -2.0 * A.gx - sdx, rawy = -sdy - 2.0 * A.gy;
+            ux = fmin(fmax(rawx * ia, -ul), ul);
+            uy = fmin(fmax(rawy * ia, -ul), ul);
+            if (a.aux.nonfinite != nullptr) {                // fmin/fmax swallow NaN: test the unclamped sums
+                const double chk = ((A.f1 + A.f2) + (A.f4 + A.f5)) + (rawx + rawy);
+                if (valid && !(fabs(chk) < CUDART_INF)) a.aux.nonfinite[env] = 1;
+            }
+        }
+        if (valid) {
+            if (a.values) {
+                TO *v = reinterpret_cast<TO *>(a.values) + grow * NFE;
+                if constexpr (PA32) {
+                    float2 *v2 = reinterpret_cast<float2 *>(v);
+                    v2[0] = make_float2((float)A.f0, (float)A.f1); v2[1] = make_float2((float)A.f2, (float)A.f3);
+                    v2[2] = make_float2((float)A.f4, (float)A.f5);
+                } else {
+                    double2 *v2 = reinterpret_cast<double2 *>(v);
+                    v2[0] = make_double2(A.f0, A.f1); v2[1] = make_double2(A.f2, A.f3); v2[2] = make_double2(A.f4, A.f5);
+                }
+            }
+            if (!last_step) {
+                // the row owner advances its own agent: next state and packed position into the other parity's copy
+                const double2 u = make_double2(ux, uy);
+                const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
+                const double4 xn = plain ? integrate_exact(xi, u, a.dt, a.var.step_scale) : integrate_variant(xi, u, i, a.dt, a.var);
+                reinterpret_cast<double4 *>(smem + a.off_xs + (par ^ 1u) * a.xs_bytes)[r] = xn;
+                if constexpr (PA32) {
+                    const double ox = xe[0].x, oy = xe[0].y;   // env origin: agent 0 before the step
+                    float *p = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem + a.off_pf + (par ^ 1u) * a.pf_bytes) + g * NP2 + (i >> 1));
+                    p[i & 1] = (float)(xn.x - ox); p[2 + (i & 1)] = (float)(xn.y - oy);
+                    if ((N & 1) && i == N - 1) { p[1] = CUDART_INF_F; p[3] = CUDART_INF_F; }
+                }
+            } else if (a.u_out) {
+                reinterpret_cast<double2 *>(a.u_out)[grow] = make_double2(ux, uy);
+            }
+        }
+
+        // ---- optional outputs (FlockAux): exact adjacency bits, degree, get_stats() ------------------------------------------------
+        if (a.aux.adj_bits != nullptr || a.aux.degree != nullptr || a.aux.min_dist != nullptr || a.aux.vel_diff != nullptr) {
+            if (valid) {
+                if (a.aux.degree) a.aux.degree[grow] = deg;
+                if (a.aux.adj_bits) for (int w = 0; w < a.aux.WB; ++w) a.aux.adj_bits[grow * a.aux.WB + w] = mrow[w * GMS];
+                if (a.aux.min_dist) {
+                    // min_j sqrt(r2) (flocking_relative.py:141-142): every neighbour is closer than every non-neighbour,
+                    // so scan the adjacency bits; a row without neighbours scans all agents
+                    double m2 = CUDART_INF;
+                    if (deg > 0) {
+                        for (int w = 0; w < nw; ++w) {
+                            unsigned b = mrow[w * GMS];
+                            while (b) {
+                                const int j = w * 32 + __ffs(b) - 1; b &= b - 1;
+                                const double dx = xi.x - xe[j].x, dy = xi.y - xe[j].y;
+                                m2 = fmin(m2, fma(dx, dx, dy * dy));
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < N; ++j) {
+                            if (j == i) continue;
+                            const double dx = xi.x - xe[j].x, dy = xi.y - xe[j].y;
+                            m2 = fmin(m2, fma(dx, dx, dy * dy));
+                        }
+                    }
+                    reinterpret_cast<TO *>(a.aux.min_dist)[grow] = (TO)sqrt(m2);
+                }
+                if (a.aux.vel_diff) {
+                    const volatile double *st = stats + g * STATS_PER_ENV;
+                    const double want = (double)(t + 1);
+                    while (st[2] < want) { }
+                    __threadfence_block();
+                    const double invN = 1.0 / (double)N;
+                    const double ex = xi.z - st[0] * invN, ey = xi.w - st[1] * invN;      // :138-140
+                    reinterpret_cast<TO *>(a.aux.vel_diff)[grow] = (TO)sqrt(fma(ex, ex, ey * ey));
+                }
+            }
+        }
+
+        // ---- dense adj_mean rows: every warp expands its own 32 rows from their exact bit masks -------------------------------
+        if (net != nullptr) {
+            __syncwarp();                                    // the lanes' mask words and 1/deg (shared memory) are complete
+            const int wr0 = tid - lane;
+            const int nrw = min(32, nrows - wr0);
+            if (nrw > 0) {
+                TO *wout = net + ((size_t)e0 * N + wr0) * N;
+                const unsigned *wm = reinterpret_cast<const unsigned *>(smem + a.off_masks) + wr0;
+                const TO *idgs = idg_s + wr0;
+                if constexpr (NC != 0) {
+                    expand_rows_const<TO, NC, GMS>(wout, wm, idgs, nrw, lane);
+                } else {
+                    constexpr int VMAX = 16 / (int)sizeof(TO);
+                    if (N % VMAX == 0) expand_rows_g<TO, VMAX>(wout, wm, idgs, N, nrw, lane);
+                    else if (VMAX == 4 && N % 2 == 0) expand_rows_g<TO, 2>(wout, wm, idgs, N, nrw, lane);
+                    else expand_rows_g<TO, 1>(wout, wm, idgs, N, nrw, lane);
+                }
+            }
+            __syncwarp();                                    // the next step rewrites the words
+        }
+    }
+    pdl_launch();
+}
+
+}  // namespace flock

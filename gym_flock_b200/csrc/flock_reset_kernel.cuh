@@ -23,6 +23,11 @@ struct RArgs {
     int max_tries;
 };
 
+
+}  // namespace flock
+#ifndef FLOCK_ARGS_ONLY
+namespace flock {
+
 __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
                                               unsigned out[4]) {
 #pragma unroll
@@ -112,3 +117,4 @@ __global__ void __launch_bounds__(RESET_THREADS) flock_reset_kernel(const RArgs 
 }
 
 }  // namespace flock
+#endif  // FLOCK_ARGS_ONLY

@@ -48,6 +48,11 @@ struct SArgs {
 
 constexpr int PREP_THREADS = 256;
 constexpr int NEEDY_CAP = 8192;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
+constexpr int SW_R = 2;         // rows per thread in the filter
+constexpr int SW_LCAP = 16;     // candidates per (row, lane)
+}  // namespace flock
+#ifndef FLOCK_ARGS_ONLY
+namespace flock {
 
 // ---- mbarrier / TMA load helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -140,9 +145,6 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a,
 //               shuffle pattern: the result does not depend on how rows are sharded over CTAs or GPUs.
 //   overflow  : a (row, lane) list holds SW_LCAP candidates; a row with a fuller list (a swarm far denser than the
 //               reference's) is recomputed by scanning all agents.
-constexpr int SW_R = 2;         // rows per thread in the filter
-constexpr int SW_LCAP = 16;     // candidates per (row, lane)
-
 template <typename TO, int LANES, bool KNN>
 __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     static_assert(LANES >= 8 && LANES <= 32, "swarm rows are split over 8..32 lanes");
@@ -327,9 +329,7 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
             A.gx += shfl_xor(A.gx, m); A.gy += shfl_xor(A.gy, m);
             deg += shfl_xor(deg, m);
         }
-        TO idg;
-        if constexpr (sizeof(TO) == 4) idg = __frcp_rn((float)max(deg, 1));
-        else idg = Tr<double>::rcp((double)max(deg, 1));
+        const TO idg = inv_deg(deg, TO(0));
 
         if (valid[r] && sub == 0) {
             if (a.values) {
@@ -398,6 +398,8 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                     for (int m = 0; m < TOPK; ++m) nb[m] = nb2[m];
                 }
             }
+            // exact order / membership among the survivors, with the reference's own keys (unfused r2, ties to the lower index)
+            knn_rerank(xi, i, reinterpret_cast<const double4 *>(xc), nb);
             if (valid[r] && sub == 0 && a.obs) {
                 TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
 #pragma unroll
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(256) flock_knn_fix_kernel(const SArgs a) {
             TopK<double> fin;
             fin.init(i);
             for (int e = 0; e < 8 * TOPK; ++e) if (si[e] != i) fin.insert(sd[e], si[e]);
+            knn_rerank(xi, i, reinterpret_cast<const double4 *>(xc), fin.id);
             // equal r2: insert keeps the earlier entry in front; entries arrive in warp order, not index order
             TO *o = reinterpret_cast<TO *>(a.obs) + ((size_t)env * N + i) * (NXS * KNN_K);
             for (int m = 0; m < KNN_K; ++m) {
@@ -481,3 +484,4 @@ __global__ void __launch_bounds__(256) flock_knn_fix_kernel(const SArgs a) {
 }
 
 }  // namespace flock
+#endif  // FLOCK_ARGS_ONLY

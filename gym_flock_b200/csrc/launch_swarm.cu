@@ -1,0 +1,56 @@
+// launch_swarm.cu -- the large-swarm kernels (prep + streaming row kernel + kNN fix-up) and the batched reset sampler.
+#include "flock_host.hpp"
+#include "flock_swarm_kernel.cuh"
+#include "flock_reset_kernel.cuh"
+
+namespace {
+template <typename TO, int LANES>
+int swarm_go(const flock::SArgs &a, bool knn, dim3 grid, size_t smem, cudaStream_t st) {
+    auto k0 = flock::flock_swarm_kernel<TO, LANES, false>;
+    auto k1 = flock::flock_swarm_kernel<TO, LANES, true>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        configured_dev = dev;
+    }
+    if (knn) k1<<<grid, 256, smem, st>>>(a); else k0<<<grid, 256, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}
+template <typename TO>
+int swarm_all(const flock::SArgs &a, int lanes, bool knn, int PB, dim3 grid, size_t smem, cudaStream_t st) {
+    flock::flock_prep_kernel<<<dim3(PB, a.E), flock::PREP_THREADS, 0, st>>>(a, sizeof(TO) == 4 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    int rc;
+    switch (lanes) {
+        case 8: rc = swarm_go<TO, 8>(a, knn, grid, smem, st); break;
+        case 16: rc = swarm_go<TO, 16>(a, knn, grid, smem, st); break;
+        default: rc = swarm_go<TO, 32>(a, knn, grid, smem, st); break;
+    }
+    if (rc || !knn) return rc;
+    // rows whose kNN search found fewer than 7 agents inside the inflated radius: one CTA per row rescans everything
+    flock::flock_knn_fix_kernel<TO><<<dim3(128, a.E), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}
+}  // namespace
+
+int launch_swarm(const flock::SArgs &a, int tbytes, int lanes, bool knn, int PB, dim3 grid, size_t smem, cudaStream_t st) {
+    return tbytes == 4 ? swarm_all<float>(a, lanes, knn, PB, grid, smem, st) : swarm_all<double>(a, lanes, knn, PB, grid, smem, st);
+}
+
+int launch_reset(const flock::RArgs &a, size_t smem, size_t smem_cap, cudaStream_t st) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(flock::flock_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        configured_dev = dev;
+    }
+    flock::flock_reset_kernel<<<a.E, flock::RESET_THREADS, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FLOCK_OK;
+}

@@ -126,18 +126,24 @@ class FlockingRelativeEnv:
         return {}
 
     def _engine(self) -> HostFlockBatch:
-        key = (self.n_agents, self.comm_radius, self.comm_radius2, self.dt, self.action_scalar, self.centralized)
+        """The device engine for the env's CURRENT attributes: every parameter a user may change between calls, as the
+        reference allows (n_agents, comm_radius(2), dt, action_scalar, centralized and the variant's own knobs), reaches
+        the kernel -- a changed n_agents rebuilds the engine, anything else is a parameter update."""
+        var = self._variant()
+        key = (self.n_agents, self.comm_radius, self.comm_radius2, self.dt, self.action_scalar, self.centralized,
+               tuple(sorted(var.items())))
         if self._eng is None or self._eng_key[0] != self.n_agents:
             if self._eng is not None:
                 self._eng.close()
             self._eng = HostFlockBatch(1, self.n_agents, comm_radius=self.comm_radius, dt=self.dt,
                                        centralized=bool(self.centralized), knn_obs=self._knn(),
                                        precision=self._precision, device=self._device,
-                                       comm_radius2=self.comm_radius2, pinned=False, **self._variant())
+                                       comm_radius2=self.comm_radius2, pinned=False,
+                                       action_scalar=float(self.action_scalar), **var)
             self._shadow = None
         elif key != self._eng_key:
             self._eng.set_params(comm_radius=self.comm_radius, comm_radius2=self.comm_radius2, dt=self.dt,
-                                 centralized=bool(self.centralized))
+                                 centralized=bool(self.centralized), action_scalar=float(self.action_scalar), **var)
         self._eng_key = key
         return self._eng
 
@@ -150,12 +156,19 @@ class FlockingRelativeEnv:
         self._x = None if value is None else np.array(value, dtype=np.float64).reshape(self.n_agents, self.nx_system)
         self._shadow = None
 
-    def _sync_device(self):
-        """Upload env.x if the user replaced or edited it since the device last saw it."""
+    def _sync_device(self, for_step: bool = False):
+        """Upload env.x if the user replaced or edited it since the device last saw it.  step() only needs the state (it
+        recomputes everything after integrating); everything else gets the helpers recomputed -- except after an in-place
+        edit the reference makes itself without recomputing them (`_helpers_stale`, FlockingLeaderEnv.reset)."""
         if self._x is None:
             raise RuntimeError("no state: call reset() or set_state(x0) first")
         if self._shadow is None or not np.array_equal(self._x, self._shadow):
-            self.compute_helpers()
+            if for_step and self._shadow is not None:
+                self._engine().upload_state(self._x[None])
+                self._shadow = self._x.copy()
+                self._helpers_stale = False
+            elif not getattr(self, "_helpers_stale", False):
+                self.compute_helpers()
 
     def _pull(self, eng):
         self.state_values = eng.values[0].copy()
@@ -171,6 +184,7 @@ class FlockingRelativeEnv:
         eng = self._engine()
         eng.set_state(self._x[None])
         self._shadow = self._x.copy()
+        self._helpers_stale = False
         self._pull(eng)
 
     def set_state(self, x0):
@@ -181,8 +195,8 @@ class FlockingRelativeEnv:
     def step(self, u):
         """flocking_relative.py:91-109."""
         assert u.shape == (self.n_agents, self.nu)
-        self._sync_device()
         eng = self._engine()
+        self._sync_device(for_step=True)
         self.u = u * self.action_scalar                      # :96 (attribute only; the kernel redoes it)
         eng.step(np.asarray(u, dtype=np.float64)[None])
         self._x = eng.x[0].copy()
@@ -264,10 +278,11 @@ class FlockingRelativeEnv:
                           d[:, :, 3], d[:, :, 1] / (r2 * r2), d[:, :, 1] / r2))
 
     def get_stats(self):
-        """flocking_relative.py:136-143."""
-        v = self._x[:, 2:4]
-        return {'vel_diffs': np.sqrt(np.sum(np.power(v - np.mean(v, axis=0), 2), axis=1)),
-                'min_dists': np.min(np.sqrt(self.r2), axis=0)}
+        """flocking_relative.py:136-143, computed by the kernel from the adjacency bits of the current state
+        (FlockAux.vel_diff / min_dist; bit-exact in the default 'fp64-exact' precision)."""
+        self._sync_device()
+        st = self._engine().get_stats()
+        return {'vel_diffs': st['vel_diffs'][0].astype(np.float64), 'min_dists': st['min_dists'][0].astype(np.float64)}
 
     def potential(self, r2):
         """flocking_relative.py:228-232 (unused by the env itself)."""
@@ -388,8 +403,8 @@ class FlockingLeaderEnv(FlockingRelativeEnv):
     def step(self, u):
         """flocking_leader.py:21-34."""
         assert u.shape == (self.n_agents, self.nu)
-        self._sync_device()
         eng = self._engine()
+        self._sync_device(for_step=True)
         self.u = u
         eng.step(np.asarray(u, dtype=np.float64)[None])
         self._x = eng.x[0].copy()
@@ -397,12 +412,17 @@ class FlockingLeaderEnv(FlockingRelativeEnv):
         self._pull(eng)
         return (self.state_values, self.state_network), self.instant_cost(), False, {}
 
+    def _set_leader_velocity(self, vel):
+        """The in-place edit of flocking_leader.py:38-39.  The reference does NOT recompute its helpers afterwards, so the
+        features it returns and the first controller() call still describe the state before the edit; step() then
+        integrates the edited state.  Reproduced: the device keeps the old helpers until the next step()."""
+        self._x[0:self.n_leaders, 2:4] = np.ones((self.n_leaders, 2)) * vel
+        self._helpers_stale = True
+
     def reset(self):
-        """flocking_leader.py:36-40: the leaders get one common random velocity AFTER the helpers were computed
-        (the reference returns the features of the state before that overwrite; so do we)."""
+        """flocking_leader.py:36-40: the leaders get one common random velocity AFTER the helpers were computed."""
         out = super().reset()
-        self._x[0:self.n_leaders, 2:4] = np.ones((self.n_leaders, 2)) * np.random.uniform(
-            low=-self.v_max, high=self.v_max, size=(1, 1))
+        self._set_leader_velocity(np.random.uniform(low=-self.v_max, high=self.v_max, size=(1, 1)))
         return out
 
 

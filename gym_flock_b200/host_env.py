@@ -48,7 +48,7 @@ class HostFlockBatch:
                  centralized: bool = True, knn_obs: bool = False, precision: str = "fp64-exact",
                  device: int = 0, lanes: int = 0, comm_radius2: float | None = None, pinned: bool = True,
                  step_scale: float = 0.0, state_scale: float = 0.0, u_clip: float = 0.0, n_leaders: int = 0,
-                 n_obstacles: int = 0):
+                 n_obstacles: int = 0, action_scalar: float = 10.0, tune: int = 0):
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         _lib.require_device()
@@ -59,7 +59,8 @@ class HostFlockBatch:
         self.knn_obs = bool(knn_obs)
         self._kw = dict(comm_radius=comm_radius, dt=dt, centralized=centralized, exact=self.exact,
                         knn_obs=knn_obs, lanes=lanes, comm_radius2=comm_radius2, step_scale=step_scale,
-                        state_scale=state_scale, u_clip=u_clip, n_leaders=n_leaders, n_obstacles=n_obstacles)
+                        state_scale=state_scale, u_clip=u_clip, n_leaders=n_leaders, n_obstacles=n_obstacles,
+                        action_scalar=action_scalar, tune=tune)
         self._params = _lib.make_params(self.E, self.N, **self._kw)
         ctx = ctypes.c_void_p()
         _lib.check(_lib.lib().flock_ctx_create(ctypes.byref(ctx), ctypes.byref(self._params),
@@ -136,3 +137,16 @@ class HostFlockBatch:
     def get_state(self) -> np.ndarray:
         _lib.check(_lib.lib().flock_ctx_get_state(self._ctx, self._p(self.x)))
         return self.x
+
+    def upload_state(self, x) -> None:
+        """x <- host state WITHOUT the pair pass: the reference's in-place edit of env.x (flocking_leader.py:38-39).
+        The cached controller action and the observation outputs keep describing the previous state until the next step."""
+        self.x[...] = np.asarray(x, dtype=np.float64).reshape(self.E, self.N, 4)
+        _lib.check(_lib.lib().flock_ctx_upload_state(self._ctx, self._p(self.x)))
+
+    def get_stats(self) -> dict:
+        """get_stats() of every env for the current state (flocking_relative.py:136-143): vel_diffs[E,N], min_dists[E,N]."""
+        vd = np.empty((self.E, self.N), self.dtype)
+        md = np.empty((self.E, self.N), self.dtype)
+        _lib.check(_lib.lib().flock_ctx_get_stats(self._ctx, self._p(vd), self._p(md)))
+        return {"vel_diffs": vd, "min_dists": md}

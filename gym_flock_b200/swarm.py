@@ -36,13 +36,16 @@ def shard_rows(n_agents: int, world: int, rank: int) -> tuple:
 class SwarmEnv:
     def __init__(self, env_id: str = "Flocking-v0", n_agents: int = 65536, precision: str = "fp32",
                  device=None, group=None, comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
-                 adjacency_mode: str = "dense", row_backend=None, lanes: int = 32, streaming: bool | None = None):
+                 adjacency_mode: str = "dense", row_backend=None, lanes: int = 32, streaming: bool | None = None,
+                 distributed: bool | None = None):
         if env_id not in _IDS:
             raise KeyError(env_id)
         self.knn = _IDS[env_id]
         self.N = int(n_agents)
         self.group = group
-        self.distributed = dist.is_available() and dist.is_initialized()
+        # distributed=False: a single-rank swarm (all rows on this GPU) even inside an initialised process group --
+        # the reference run the multi-rank checks compare against
+        self.distributed = (dist.is_available() and dist.is_initialized()) if distributed is None else bool(distributed)
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.world = dist.get_world_size(group) if self.distributed else 1
         self.lo, self.hi = shard_rows(self.N, self.world, self.rank)
@@ -139,7 +142,11 @@ class SwarmEnv:
     def _gather_actions(self, u_full):
         """In-place all-gather of the rows each rank just computed (equal shards, rank order = row order)."""
         if self.world > 1 and not self._skip_gather:
-            dist.all_gather_into_tensor(u_full, u_full[self.lo:self.hi].clone(), group=self.group)
+            mine = u_full[self.lo:self.hi]
+            if u_full.is_cuda:      # NCCL gathers in place (send buffer = this rank's slice of the receive buffer)
+                dist.all_gather_into_tensor(u_full, mine, group=self.group)
+            else:                   # gloo (CPU tests) wants a separate send buffer
+                dist.all_gather_into_tensor(u_full, mine.clone(), group=self.group)
 
     def _observation(self):
         return (self.obs if self.knn else self.values), self.network

@@ -9,6 +9,9 @@ Layout (all contiguous):
   x[E,N,4] float64 (px,py,vx,vy) -- canonical state, double in every precision mode
   u[E,N,2] float64 in [-1,1]
   values[E,N,6], network[E,N,N], reward[E], obs[E,N,28]: float64 ('fp64', 'fp64-exact') or float32 ('fp32')
+  adjacency_mode='bitmask': instead of the dense network, adj_bits[E,N,ceil(N/32)] int32 (bit j&31 of word j>>5 of row i:
+  agents i and j are neighbours) and degree[E,N] int32 -- 32x fewer bytes; `aggregate()` consumes them directly.
+  nonfinite[E] int32: set when an env produced NaN/Inf (coincident agents give 0/0 in the reference too).
 """
 from __future__ import annotations
 
@@ -28,13 +31,17 @@ class FlockVecEnv:
                  precision: str = "fp32", device: str | int | torch.device = "cuda:0",
                  comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
                  adjacency_mode: str = "dense", max_episode_steps: int = 1000, lanes: int = 0,
-                 rows: tuple | None = None):
+                 rows: tuple | None = None, action_scalar: float = 10.0, step_scale: float = 0.0, state_scale: float = 0.0,
+                 u_clip: float = 0.0, n_leaders: int = 0, n_obstacles: int = 0, tune: int = 0):
         if env_id not in _IDS:
             raise KeyError(f"unknown env id {env_id!r}; provided: {sorted(_IDS)}")
         if precision not in _PREC:
             raise ValueError(f"precision must be one of {sorted(_PREC)}")
-        if adjacency_mode not in ("dense", "none"):
-            raise ValueError("adjacency_mode must be 'dense' (reference layout) or 'none' (skip the [E,N,N] write)")
+        if adjacency_mode not in ("dense", "bitmask", "none"):
+            raise ValueError("adjacency_mode must be 'dense' (reference layout), 'bitmask' (exact adjacency bits + degree) "
+                             "or 'none' (skip the adjacency output)")
+        if adjacency_mode == "bitmask" and rows is not None:
+            raise ValueError("adjacency_mode='bitmask' is offered for full rows only")
         if not torch.cuda.is_available():
             raise RuntimeError("FlockVecEnv needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.lib()
@@ -50,6 +57,9 @@ class FlockVecEnv:
         self.adjacency_mode = adjacency_mode
         self.rows = rows
         self.lanes = int(lanes)
+        # flocking variants through the same kernel (FlockParams.step_scale / state_scale / u_clip / n_leaders / n_obstacles)
+        self._variant = dict(action_scalar=float(action_scalar), step_scale=float(step_scale), state_scale=float(state_scale),
+                             u_clip=float(u_clip), n_leaders=int(n_leaders), n_obstacles=int(n_obstacles), tune=int(tune))
         E, N, dev = self.E, self.N, self.device
         f64 = torch.float64
         self._x = [torch.zeros(E, N, 4, dtype=f64, device=dev) for _ in range(2)]
@@ -59,8 +69,15 @@ class FlockVecEnv:
         self.network = torch.zeros(E, N, N, dtype=self.dtype, device=dev) if adjacency_mode == "dense" else None
         self.reward = torch.zeros(E, dtype=self.dtype, device=dev)
         self.obs = torch.zeros(E, N, 28, dtype=self.dtype, device=dev) if self.knn else None
+        self.nonfinite = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.words = int(self.lib.flock_adj_words(N))
+        self.adj_bits = torch.zeros(E, N, self.words, dtype=torch.int32, device=dev) if adjacency_mode == "bitmask" else None
+        self.degree = torch.zeros(E, N, dtype=torch.int32, device=dev) if adjacency_mode == "bitmask" else None
+        self._aux = _lib.FlockAux(self.nonfinite.data_ptr(),
+                                  self.adj_bits.data_ptr() if self.adj_bits is not None else None,
+                                  self.degree.data_ptr() if self.degree is not None else None, None, None)
         self.elapsed = 0
-        self._fn_step = self.lib.flock_step_f64 if self.dtype == torch.float64 else self.lib.flock_step_f32
+        self._fn_step = self.lib.flock_step_aux_f64 if self.dtype == torch.float64 else self.lib.flock_step_aux_f32
         self._fn_roll = self.lib.flock_rollout_f64 if self.dtype == torch.float64 else self.lib.flock_rollout_f32
         self._u_valid = False
         self._refresh_params()
@@ -69,7 +86,7 @@ class FlockVecEnv:
     def _refresh_params(self):
         self._params = _lib.make_params(self.E, self.N, comm_radius=self.comm_radius, dt=self.dt,
                                         centralized=self.centralized, exact=self.exact, knn_obs=self.knn,
-                                        rows=self.rows, lanes=self.lanes)
+                                        rows=self.rows, lanes=self.lanes, **self._variant)
         self._pp = ctypes.byref(self._params)
 
     @staticmethod
@@ -89,16 +106,19 @@ class FlockVecEnv:
         return self._u[self._cur]
 
     def _observation(self):
-        return (self.obs if self.knn else self.values), self.network
+        """(values | obs, network): the reference's observation tuple; in 'bitmask' mode the second item is adj_bits."""
+        return (self.obs if self.knn else self.values), (self.adj_bits if self.adjacency_mode == "bitmask" else self.network)
 
-    def _launch(self, x_in, u_in, x_out, u_next, want_obs=True):
+    def _launch(self, x_in, u_in, x_out, u_next, want_obs=True, aux=None):
+        if aux is None:
+            aux = self._aux if want_obs else _lib.FlockAux(self.nonfinite.data_ptr(), None, None, None, None)
         with torch.cuda.device(self.device):
             _lib.check(self._fn_step(self._pp, self._ptr(x_in), self._ptr(u_in), self._ptr(x_out),
                                      self._ptr(self.values) if want_obs else None,
                                      self._ptr(self.network) if want_obs else None,
                                      self._ptr(self.reward) if want_obs else None,
                                      self._ptr(u_next), self._ptr(self.obs) if want_obs else None,
-                                     self._stream()))
+                                     ctypes.byref(aux), self._stream()))
 
     # ---- API -----------------------------------------------------------------------------------------------
     def reset(self, x0=None, seed: int | None = None):
@@ -178,6 +198,12 @@ class FlockVecEnv:
         Observation tensors hold the last step; rewards_out[steps,E] (optional) gets every step's reward."""
         if not self._u_valid:
             self.controller()
+        if self.adjacency_mode == "bitmask":         # the fused rollout has no bit output: step by step
+            for t in range(int(steps)):
+                self.step(None)
+                if rewards_out is not None:
+                    rewards_out[t].copy_(self.reward)
+            return self._observation(), self.reward
         a, b = self._cur, self._cur ^ 1
         fin = ctypes.c_int32(0)
         with torch.cuda.device(self.device):
@@ -188,6 +214,37 @@ class FlockVecEnv:
         self._cur = b if fin.value else a
         self.elapsed += int(steps)
         return self._observation(), self.reward
+
+    def get_stats(self) -> dict:
+        """get_stats() of every env for the current state (flocking_relative.py:136-143), computed by the kernel:
+        {'vel_diffs': [E,N], 'min_dists': [E,N]} in the observation dtype."""
+        vd = torch.empty(self.E, self.N, dtype=self.dtype, device=self.device)
+        md = torch.empty(self.E, self.N, dtype=self.dtype, device=self.device)
+        aux = _lib.FlockAux(None, None, None, md.data_ptr(), vd.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn_step(self._pp, self._ptr(self.x), None, None, None, None, None, None, None,
+                                     ctypes.byref(aux), self._stream()))
+        return {"vel_diffs": vd, "min_dists": md}
+
+    def aggregate(self, filter_len: int, prev: torch.Tensor | None = None, pool: str = "mean",
+                  signal: torch.Tensor | None = None) -> torch.Tensor:
+        """Graph-signal aggregation on the current adjacency, from its bits (adjacency_mode='bitmask'), never the dense
+        [N,N] (gym_flock/envs/old/flocking_multi.py:180-196).  signal[E,N,F] defaults to `values`.
+          prev given   : delayed aggregation, out[i] = [signal[i] | pool_{j in N(i)} prev[j][:F*(L-1)]]
+          prev is None : K-hop, out[i] = [signal | S signal | ... | S^(L-1) signal], S = D^-1 A ('mean') or A ('sum')"""
+        if self.adj_bits is None:
+            raise RuntimeError("aggregate() needs adjacency_mode='bitmask'")
+        x = self.values if signal is None else signal.to(device=self.device, dtype=self.dtype).contiguous()
+        F, L = int(x.shape[-1]), int(filter_len)
+        out = torch.empty(self.E, self.N, F * L, dtype=self.dtype, device=self.device)
+        if prev is not None:
+            prev = prev.to(device=self.device, dtype=self.dtype).contiguous()
+            assert prev.shape == out.shape, (prev.shape, out.shape)
+        fn = self.lib.flock_aggregate_f64 if self.dtype == torch.float64 else self.lib.flock_aggregate_f32
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._pp, self._ptr(x), F, self._ptr(prev), self._ptr(self.adj_bits), L,
+                          {"mean": 0, "sum": 1}[pool], self._ptr(out), self._stream()))
+        return out
 
     def close(self):
         pass

@@ -18,7 +18,9 @@
  * Conventions
  *   - State-side arrays are ALWAYS double: x[E][N][4] = (px,py,vx,vy), u[E][N][2] in [-1,1].
  *   - Observation-side arrays (values, network, reward, obs) are double for *_f64 and float for *_f32.
- *   - All device buffers are caller-owned, contiguous, 16-byte aligned.  The library allocates nothing
+ *   - All device buffers are caller-owned, contiguous, 16-byte aligned (`reward`: element aligned; in row-sharded calls,
+ *     where a caller may pass shard-sized buffers shifted back by row_lo rows, `values` needs 8 bytes and `network` only
+ *     element alignment).  The library allocates nothing
  *     behind device-pointer entry points; they are asynchronous on `stream` (a cudaStream_t passed as
  *     void*), re-entrant, and never synchronise.
  *   - Every entry point returns 0 on success or a negative FLOCK_E* code; it never throws or exits.
@@ -34,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FLOCK_ABI_VERSION 3
+#define FLOCK_ABI_VERSION 4
 
 /* flags */
 #define FLOCK_CENTRALIZED   0x1   /* controller(centralized=True), flocking_relative.py:200-206 */
@@ -63,7 +65,8 @@ typedef struct FlockParams {
                              *   addressed by GLOBAL row but only rows [row_lo,row_hi) are ever touched, so a caller
                              *   may pass shard-sized buffers shifted back by row_lo rows. */
     int32_t lanes;          /* threads cooperating on one row (power of two <= 32); 0 = choose */
-    int32_t reserved;       /* 0 (tuning / diagnostics word, see FLOCK_TUNE in gym_flock_b200/_lib.py) */
+    int32_t reserved;       /* 0.  (Diagnostics word of tools/ and bench.py A/B runs -- CTA size, phase switches, envs per
+                             *   CTA; a non-zero value can switch whole phases off, so bindings must pass 0.) */
     /* ---- flocking variants through the same kernel; all zero = FlockingRelative / Flocking ---- */
     double  step_scale;     /* step(): a = u * step_scale.  0 = action_scalar (flocking_relative.py:96);
                              *   1.0 for FlockingLeader (self.u = u, flocking_leader.py:24); 6.0 for FlockingStochastic */
@@ -101,8 +104,61 @@ int flock_step_f32(const FlockParams *p, const double *x_in, const double *u_in,
                    float *values, float *network, float *reward, double *u_next, float *obs,
                    void *stream);
 
+/* Optional extra outputs of one step (SURVEY.md 5 "aux", 8f #4).  Every pointer is nullable; pass aux = NULL for none.
+ * Device buffers, caller-owned; observation-side types follow the entry point (double for *_f64, float for *_f32). */
+typedef struct FlockAux {
+    int32_t  *nonfinite;    /* [E]  set to 1 when a feature, state or action of the env is NaN / Inf (coincident agents give
+                             *      0/0 in the reference, flocking_relative.py:124).  Never cleared by the library. */
+    uint32_t *adj_bits;     /* [E][N][flock_adj_words(N)]  the exact adjacency as bits: bit (j & 31) of word (j >> 5) of row i
+                             *      is r2[i][j] < comm_radius2 (:117).  The 'bitmask' adjacency mode: 32x smaller than the
+                             *      dense fp32 network; with network = NULL the N^2 write is skipped altogether.  The call
+                             *      then runs one thread per row (lanes is ignored). */
+    int32_t  *degree;       /* [E][N]  neighbours per row (the divisor of adj_mean, before the 0 -> 1 fix, :120-121) */
+    void     *min_dist;     /* [E][N]  get_stats()['min_dists']: min_j sqrt(r2[i][j]) (:141-142) */
+    void     *vel_diff;     /* [E][N]  get_stats()['vel_diffs']: |v_i - mean_j v_j| (:138-140) */
+} FlockAux;
+
+/* words per row of FlockAux.adj_bits: ceil(n_agents / 32) */
+int flock_adj_words(int32_t n_agents);
+
+/* flock_step_* with the optional outputs above.  Replaces additionally: FlockingRelativeEnv.get_stats(). */
+int flock_step_aux_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out,
+                       double *values, double *network, double *reward, double *u_next, double *obs,
+                       const FlockAux *aux, void *stream);
+int flock_step_aux_f32(const FlockParams *p, const double *x_in, const double *u_in, double *x_out,
+                       float *values, float *network, float *reward, double *u_next, float *obs,
+                       const FlockAux *aux, void *stream);
+
+/* Graph-signal aggregation on the adjacency the step produced, from its BITS (FlockAux.adj_bits; never the dense [N,N]):
+ *   x    [E][N][F]      the nodes' current features (e.g. state_values, F = 6)
+ *   prev [E][N][F*L]    last step's aggregate, or NULL
+ *   out  [E][N][F*L]    prev != NULL (delayed aggregation, gym_flock/envs/old/flocking_multi.py:180-196):
+ *                         out[i] = [ x[i] | pool_{j in N(i)} prev[j][0 : F*(L-1)] ]
+ *                       prev == NULL (K-hop of the current signal): out[i] = [ x[i] | (S x)[i] | ... | (S^(L-1) x)[i] ]
+ *   pool  FLOCK_POOL_MEAN: np.nanmean over the connected senders (:36, :262-265; S = D^-1 A = state_network with
+ *         mean_pooling; a node without neighbours receives 0), FLOCK_POOL_SUM: S = A.
+ * f64 reproduces NumPy bit for bit (ascending-j sums, true divide).  out must not alias prev or x.  p: n_envs, n_agents. */
+#define FLOCK_POOL_MEAN 0
+#define FLOCK_POOL_SUM  1
+int flock_aggregate_f64(const FlockParams *p, const double *x, int32_t F, const double *prev, const uint32_t *adj_bits,
+                        int32_t L, int32_t pool, double *out, void *stream);
+int flock_aggregate_f32(const FlockParams *p, const float *x, int32_t F, const float *prev, const uint32_t *adj_bits,
+                        int32_t L, int32_t pool, float *out, void *stream);
+
+/* The sheep controller of the shepherding env (gym_flock/envs/shepherding/shepherding.py:164-178): the same all-pairs
+ * inverse-distance shape as the flocking potential.  out[e][i] = sum_j weights[j] * (p_i - p_j) / r2_ij over the agents with
+ * r2 <= cutoff_r2 (2.0 in the reference; the diagonal is excluded).  pos[E][N][stride] doubles with x, y in columns 0, 1
+ * (stride = 3 for the reference's (x, y, heading) state); weights[N] per SOURCE agent (force_weights, :50); out[E][N][2].
+ * f64 follows the reference's operation order (bit-exact); the caller keeps rows n_shepherds.. (:178). */
+int flock_repulsion_f64(const FlockParams *p, const double *pos, int32_t stride, const double *weights, double cutoff_r2,
+                        double *out, void *stream);
+int flock_repulsion_f32(const FlockParams *p, const double *pos, int32_t stride, const float *weights, double cutoff_r2,
+                        float *out, void *stream);
+
 /* `steps` fused steps with the internal controller (the driver loop {u=controller(); step(u)}),
- * launched back to back on `stream` from C (no per-step host round trip).
+ * without a per-step host round trip.  Batches of small envs (n_agents <= 512, full rows, no FLOCK_EXACT_ORDER) run as
+ * ONE persistent launch that keeps the state in shared memory between steps (every step still writes all of its
+ * outputs); everything else is `steps` launches queued back to back.  Both produce the bits of `steps` flock_step_* calls.
  *   x_a / x_b: ping-pong state buffers, x_a holds the start state; returns in *final_in_b whether the
  *              final state is in x_b (1) or x_a (0).   u_a / u_b: ping-pong actions; u_a must hold
  *              controller(x_a) on entry (as produced by a previous flock_step_* call's u_next).
@@ -162,6 +218,12 @@ int  flock_ctx_step(FlockCtx *ctx, const double *u_host,
 /* controller(centralized): copies the controller action for the CURRENT state to u_host [E][N][2]. */
 int  flock_ctx_controller(FlockCtx *ctx, int32_t centralized, double *u_host);
 int  flock_ctx_get_state(FlockCtx *ctx, double *x_host);
+/* x <- host state WITHOUT running the pair pass (the reference's in-place edit of env.x, e.g. flocking_leader.py:38-39):
+ * the cached controller action and the observation-side outputs keep describing the previous state until the next step. */
+int  flock_ctx_upload_state(FlockCtx *ctx, const double *x_host);
+/* get_stats() for the current state (flocking_relative.py:136-143): vel_diffs[E][N], min_dists[E][N] in the context's
+ * observation dtype; either may be NULL. */
+int  flock_ctx_get_stats(FlockCtx *ctx, void *vel_diffs_host, void *min_dists_host);
 
 #ifdef __cplusplus
 }

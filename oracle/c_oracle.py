@@ -77,6 +77,23 @@ def knn_obs(x, k=7):
     return obs
 
 
+def rows(x, row_idx, comm_radius=0.9, centralized=True, knn=0, want_network=True):
+    """A subset of rows of ONE env x[N,4] (giant-swarm tests): dict of values[R,6], deg[R], adj_mean[R,N], u[R,2],
+    obs[R,4*knn], r2_sorted[R,knn+2] -- the same per-row C functions as the full-matrix entry points."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    idx = np.ascontiguousarray(row_idx, dtype=np.int32)
+    n, r = x.shape[0], idx.shape[0]
+    values = np.empty((r, 6)); deg = np.empty(r); u = np.empty((r, 2))
+    net = np.empty((r, n)) if want_network else None
+    obs = np.empty((r, 4 * knn)) if knn else None
+    r2s = np.empty((r, knn + 2)) if knn else None
+    lib().flk_rows_f64(_p(x), ctypes.c_int(n), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.c_int(r),
+                       ctypes.c_double(comm_radius), ctypes.c_double(comm_radius * comm_radius),
+                       ctypes.c_int(int(centralized)), ctypes.c_int(knn), _p(values), _p(deg), _p(net), _p(u), _p(obs),
+                       _p(r2s))
+    return {"values": values, "deg": deg, "adj_mean": net, "u": u, "obs": obs, "r2_sorted": r2s}
+
+
 def rollout(x0, steps, comm_radius=0.9, dt=0.01, centralized=True, knn=0, want_network=True, nthreads=0):
     """x0[E,N,4] (or [N,4]) -> dict of final x, values, adj_mean, u (last action), rewards[E,steps], obs."""
     x = np.array(x0, dtype=np.float64, order="C").copy()

@@ -11,10 +11,11 @@ installs three shims -- stub ``gym``/``gym.spaces``/``gym.utils.seeding``
 modules, a stub ``matplotlib.pyplot`` and ``np.Inf = np.inf`` -- and then
 executes the two reference files *by path*, without touching them.
 
-Search order for the reference tree: ``$GYM_FLOCK_REF``, ``/root/reference``.
-The tree does not exist on the GPU box; ``available()`` is False there and
-callers fall back to the committed golden vectors + the restatements in
-``oracle/flock_numpy.py`` / ``oracle/flock_oracle.c``.
+Search order for the reference tree: ``$GYM_FLOCK_REF``, ``/root/reference``,
+``<repo>/baseline/_ref`` (the git-ignored ``pip install --target`` copy of the
+unmodified reference that travels to the GPU box).  Where none
+exists ``available()`` is False and callers fall back to the committed golden
+vectors + the restatements in ``oracle/flock_numpy.py`` / ``oracle/flock_oracle.c``.
 """
 from __future__ import annotations
 
@@ -30,7 +31,8 @@ _cache: dict = {}
 
 
 def reference_root() -> str | None:
-    for cand in (os.environ.get("GYM_FLOCK_REF"), "/root/reference"):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("GYM_FLOCK_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
         if cand and all(os.path.isfile(os.path.join(cand, f)) for f in _HOT_FILES):
             return cand
     return None

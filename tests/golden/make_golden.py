@@ -125,7 +125,37 @@ def run_variant(which, n, seed):
     return out
 
 
+def leader_reset(n=20, seed=41):
+    """FlockingLeaderEnv.reset() of the reference (flocking_leader.py:36-40) followed by controller() / step(): the
+    leaders' velocities are overwritten AFTER compute_helpers(), so the returned features and the first controller()
+    describe the state before the overwrite.  x_pre is what the base-class reset() leaves with the same seed (the
+    leader draw comes after the rejection loop)."""
+    Rel, _ = ref_loader.load()
+    env = ref_loader.load_variant("flocking_leader", "FlockingLeaderEnv")()
+    env.params_from_cfg(ref_loader.CfgSection(comm_radius=0.9, n_agents=n, v_max=5.0, dt=0.01))
+    np.random.seed(seed)
+    Rel.reset(env)
+    x_pre = env.x.copy()
+    np.random.seed(seed)
+    values, net = env.reset()
+    x_post = env.x.copy()
+    assert np.array_equal(x_pre[:, :2], x_post[:, :2]) and np.array_equal(x_pre[env.n_leaders:], x_post[env.n_leaders:])
+    out = {"x_pre": x_pre, "x_post": x_post, "leader_vel": np.array(x_post[0, 2]), "values_reset": values.copy()}
+    u = env.controller()
+    out["u_first"] = u.copy()
+    for t in range(1, 4):
+        (values, net), r, _, _ = env.step(u)
+        out[f"x_{t}"] = env.x.copy(); out[f"values_{t}"] = values.copy()
+        u = env.controller()
+        out[f"u_{t}"] = u.copy()
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "reset_leader_n20.npz"), **leader_reset())
+    print("wrote reset_leader_n20")
+    if "--only-new" in sys.argv:
+        return
     for which, n, seed in (("leader", 100, 31), ("stochastic", 100, 32), ("leader", 20, 33), ("stochastic", 33, 34),
                            ("obstacle", 100, 0), ("obstacle", 40, 35)):
         np.savez_compressed(os.path.join(HERE, f"variant_{which}_n{n}.npz"), **run_variant(which, n, seed))

@@ -10,7 +10,7 @@ RECORD = (1, 2, 50, 100, 200)
 
 def golden_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("smoke", "variant")))
+                  if not os.path.basename(p).startswith(("smoke", "variant", "reset")))
 
 
 def load(name):

@@ -23,11 +23,12 @@ def test_every_declared_symbol_is_exported(L):
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b(flock_[a-z0-9_]+)\s*\(", hdr))
     assert {"flock_step_f64", "flock_step_f32", "flock_rollout_f64", "flock_rollout_f32", "flock_ctx_create",
-            "flock_ctx_step", "flock_ctx_controller", "flock_last_error"} <= names
+            "flock_ctx_step", "flock_ctx_controller", "flock_last_error", "flock_step_aux_f32", "flock_aggregate_f64",
+            "flock_repulsion_f64", "flock_ctx_get_stats", "flock_ctx_upload_state", "flock_adj_words"} <= names
     for n in sorted(names):
         assert hasattr(L, n), n
     from gym_flock_b200 import _lib
-    assert L.flock_abi_version() == _lib.ABI_VERSION == 3
+    assert L.flock_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_params_struct_layout_matches_header():
@@ -35,6 +36,26 @@ def test_params_struct_layout_matches_header():
     assert ctypes.sizeof(FlockParams) == 96
     assert FlockParams.comm_radius.offset == 8 and FlockParams.flags.offset == 40 and FlockParams.lanes.offset == 56
     assert FlockParams.step_scale.offset == 64 and FlockParams.n_leaders.offset == 88
+
+
+def test_aux_struct_layout_and_validation(L):
+    from gym_flock_b200 import _lib
+    assert ctypes.sizeof(_lib.FlockAux) == 40 and _lib.FlockAux.vel_diff.offset == 32
+    assert L.flock_adj_words(100) == 4 and L.flock_adj_words(32) == 1 and L.flock_adj_words(33) == 2
+    buf = np.zeros(64, dtype=np.float64)
+    ptr = ctypes.c_void_p((buf.ctypes.data + 15) & ~15)
+    aux = _lib.FlockAux(ptr.value + 2, None, None, None, None)                 # misaligned int32 flag buffer
+    p = _lib.make_params(1, 4)
+    assert L.flock_step_aux_f64(ctypes.byref(p), ptr, None, None, None, None, None, None, None, ctypes.byref(aux), None) == -2
+    assert p.reserved == 0                                                      # bindings never set the diagnostics word
+    assert L.flock_aggregate_f64(ctypes.byref(p), ptr, 0, None, ptr, 2, 0, ptr, None) == -1       # F < 1
+    assert L.flock_aggregate_f64(ctypes.byref(p), ptr, 6, None, ptr, 2, 7, ctypes.c_void_p(ptr.value + 64), None) == -1   # pool
+    assert L.flock_repulsion_f64(ctypes.byref(p), ptr, 1, ptr, 2.0, ptr, None) == -1               # stride < 2
+    os.environ["FLOCK_TUNE"] = "4096"                                          # a stray environment variable changes nothing
+    try:
+        assert _lib.make_params(1, 4).reserved == 0
+    finally:
+        del os.environ["FLOCK_TUNE"]
 
 
 def test_argument_validation_needs_no_gpu(L):

@@ -44,7 +44,7 @@ def test_exact_mode_batch_vs_oracle(e, n, cen, knn):
     from gym_flock_b200.synthetic import initial_states
     from oracle import c_oracle
     x0 = initial_states(e, n, seed=777, min_dist=0.1 if n <= 100 else 0.0)
-    steps = 200 if n <= 257 else 20
+    steps = 200                    # north_star: "over a 200-step rollout", also at N = 1000 (BASELINE config 4)
     ref = c_oracle.rollout(x0, steps, centralized=cen, knn=7 if knn else 0)
     eng = HostFlockBatch(e, n, centralized=cen, knn_obs=knn, precision="fp64-exact")
     eng.set_state(x0)

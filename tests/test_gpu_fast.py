@@ -3,7 +3,7 @@ teacher-forced at points of the reference trajectory + a free-running 200-step r
 import numpy as np
 import pytest
 
-from parity_util import TOL, check_pass, normwise
+from parity_util import TOL, check_knn_obs, check_pass, normwise
 
 pytestmark = pytest.mark.gpu
 
@@ -16,6 +16,9 @@ CASES = [  # (E, N, centralized, knn, lanes)
     (40, 12, True, False, 1), (27, 20, False, False, 1),
     # kNN with one thread per row (fp32 mode: packed-key min/max network), incl. fewer than 7 neighbours and odd N
     (9, 100, True, True, 1), (4, 7, True, True, 1), (3, 9, False, True, 1), (2, 257, True, True, 1),
+    # whole envs per CTA (flock_group_kernel): compile-time sizes N = 100 / 50, a last CTA with fewer envs, odd N, N = 512
+    (7, 100, True, False, 1), (11, 50, False, False, 1), (13, 50, True, True, 1), (3, 101, True, True, 1), (2, 512, True, False, 1),
+    (1, 1, True, False, 1), (600, 10, True, False, 1),
 ]
 
 
@@ -50,11 +53,9 @@ def test_teacher_forced_and_free_running(precision, e, n, cen, knn, lanes):
             for kk, vv in errs.items():
                 worst[kk] = max(worst.get(kk, 0), vv)
             if knn and n >= 7:
-                ref_obs = c_oracle.knn_obs(x_ref[k])
-                # neighbour ORDER may swap when two r2 differ by less than the working precision
-                same = np.isclose(eng.obs[k], ref_obs, rtol=0, atol=TOL[kind] * max(1.0, np.max(np.abs(ref_obs))))
-                rows_ok = same.all(axis=1)
-                assert rows_ok.mean() > 0.98, rows_ok.mean()
+                # every row, exactly the reference's neighbours in the reference's order (the fast modes re-rank their
+                # survivors with the reference's own keys); only a provable membership near-tie is exempt
+                worst["knn_near_tie_rows"] = max(worst.get("knn_near_tie_rows", 0), check_knn_obs(eng.obs[k], x_ref[k], kind))
 
     # (ii) free-running with the device-side controller
     print("teacher-forced worst errors:", worst)

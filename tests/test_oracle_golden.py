@@ -120,3 +120,22 @@ def test_numpy_port_variants_match_reference_golden(name):
             assert np.array_equal(u, g[f"u_{t}"]), t
             assert np.array_equal(h["values"], g[f"values_{t}"]), t
     assert np.array_equal(rewards, g["rewards"])
+
+
+def test_c_oracle_row_subset_equals_full_matrix():
+    """flk_rows_f64 (what the giant-swarm GPU tests compare against) is the same arithmetic as the pinned full-matrix
+    entry points: bit-equal on a row sample."""
+    from gym_flock_b200.synthetic import initial_state
+    from oracle import c_oracle
+    n = 300
+    x = initial_state(n, seed=5, law="density", min_dist=0.1)
+    idx = np.array([0, 1, 17, 150, 298, 299], dtype=np.int32)
+    for cen in (True, False):
+        part = c_oracle.rows(x, idx, centralized=cen, knn=7)
+        h = c_oracle.helpers(x)
+        assert np.array_equal(part["values"], h["values"][idx])
+        assert np.array_equal(part["adj_mean"], h["adj_mean"][idx])
+        assert np.array_equal(part["deg"], h["adj"][idx].sum(1))
+        assert np.array_equal(part["u"], c_oracle.controller(x, centralized=cen)[idx])
+        assert np.array_equal(part["obs"], c_oracle.knn_obs(x)[idx])
+        assert np.all(np.diff(part["r2_sorted"], axis=1) >= 0)
