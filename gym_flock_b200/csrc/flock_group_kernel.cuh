@@ -34,6 +34,8 @@ struct GArgs {
     void *values, *network, *reward, *rewards_all, *obs;
     AuxOut aux;
     int E, N, G, steps;
+    int n_main, G_tail;       // CTAs [0, n_main) own G envs each; the CTAs after them own G_tail (< G) envs each -- the last,
+                              // partial round of the grid is spread over all SMs instead of leaving most of them idle
     int NP2;                  // pair slots per env in the packed fp32 position array
     int W;                    // 32-bit candidate words per row
     int centralized;
@@ -143,8 +145,9 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
     const int N = NC ? NC : a.N;
     const int NP2 = NC ? (NC + 1) / 2 : a.NP2;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int e0 = blockIdx.x * a.G;
-    const int genv = min(a.G, a.E - e0);
+    const int bid = blockIdx.x;
+    const int e0 = (bid < a.n_main) ? bid * a.G : a.n_main * a.G + (bid - a.n_main) * a.G_tail;
+    const int genv = min((bid < a.n_main) ? a.G : a.G_tail, a.E - e0);
     const int nrows = genv * N;                            // rows (agents) of this CTA
     const bool valid = tid < nrows;
     const int r = valid ? tid : 0;                         // idle threads shadow row 0 and store nothing
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             }
         }
 
+        if (tid - lane >= nrows) continue;                // a warp without rows (a CTA of the tail round) only keeps the barrier
         const double4 *xe = xs + g * N;
         const double4 xi = xe[i];
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);

@@ -3,16 +3,18 @@
 // Same algorithm as flock_env_kernel.cuh ("filter then refine"), restructured for N up to 2^16+ agents per env:
 //
 //   flock_prep_kernel  (O(N)) : x' = integrate(x_in, u_in) for ALL agents -> x_out; packed fp32 positions relative
-//                               to the env origin -> scratch; deterministic two-stage reduction of the velocity sums
-//                               (alignment identity, reward) -> scratch.       flocking_relative.py:96-105,145-147
+//                               to the env origin -> scratch; per-block partial velocity sums -> scratch (every row CTA
+//                               adds them up in block order: deterministic, shard independent, no tickets or counters to
+//                               clear between launches).                        flocking_relative.py:96-105,145-147
 //   flock_swarm_kernel (rows) : a CTA owns 256/LANES rows of one env.  The packed fp32 positions of ALL agents stream
 //                               through shared memory in tiles, double buffered with 1-D TMA bulk loads completing on
 //                               mbarriers (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes).
 //                               Per tile: phase A (packed f32x2 filter, conservative threshold, two rows per thread)
 //                               appends the few candidates to per-thread lists; after the last tile phase B refines
-//                               them in fp64 (x_j read through L2).  The dense adj_mean rows are zero-filled by the
-//                               owning warp with direct streaming stores, one slice per tile, and the non-zeros are
-//                               stored over them at the end.                     :111-134,194-226, flocking.py:20-24
+//                               them in fp64 (x_j read through L2).  The dense adj_mean rows (256 KB each) are zero-filled
+//                               by dedicated FILL WARPS of the CTA with direct streaming stores while the other warps
+//                               filter (the store queue never blocks a filtering warp); one block barrier later the few
+//                               non-zeros are stored over them.                  :111-134,194-226, flocking.py:20-24
 //
 // The row arithmetic does not depend on how rows are sharded over CTAs or GPUs.  Exact-order (NumPy bit-exact) mode
 // is not offered here: its sequential all-j sums belong to the env-resident kernel (N up to a few thousand).
@@ -31,10 +33,8 @@ struct SArgs {
     void *reward;
     void *obs;
     float4 *pf;             // scratch: packed positions [E][NP2]
-    double *partials;       // scratch: [E][PB][4]
-    double *totals;         // scratch: [E][8]  (ref vx, ref vy, sum vx, sum vy, reward, ref px, ref py, pad)
-    unsigned *counters;     // scratch: [E] tickets of the two-stage reduction (zero between launches)
-    unsigned *needy_cnt;    // scratch: [E] rows whose kNN search needs a full rescan (cleared every step)
+    double *partials;       // scratch: [E][PB][4]  per prep block: sum (v - ref), sum (v - ref)^2
+    unsigned *needy_cnt;    // scratch: [E] rows whose kNN search needs a full rescan (cleared by the prep kernel)
     unsigned *needy_rows;   // scratch: [E][NEEDY_CAP]
     int E, N, NP2, PB;
     int row_lo, row_hi;
@@ -43,13 +43,16 @@ struct SArgs {
     int centralized;
     double R, R2, Rm, thrC, dt, ascale, inv_ascale;
     StepVariant var;
-    unsigned off_tiles, off_lists, off_bar;
+    unsigned off_tiles, off_lists, off_bar, off_tot;
+    int fill_warps;         // warps per CTA that only zero-fill the CTA's dense rows (0 when network == NULL)
 };
 
 constexpr int PREP_THREADS = 256;
 constexpr int NEEDY_CAP = 8192;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
 constexpr int SW_R = 2;         // rows per thread in the filter
 constexpr int SW_LCAP = 16;     // candidates per (row, lane)
+constexpr int SW_THREADS = 256; // filtering threads per CTA (fill warps come on top)
+constexpr int SW_FILL_WARPS = 2;
 }  // namespace flock
 #ifndef FLOCK_ARGS_ONLY
 namespace flock {
@@ -82,10 +85,11 @@ __device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, unsi
 }
 
 // ---- O(N) preparation ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a, const int want_reward_f32) {
+__global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a) {
     const int env = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
     const int N = a.N;
     const size_t e0 = (size_t)env * N;
+    pdl_wait();
     const double4 ref = ld_state(a.x_in + e0 * 4);          // origin / reference velocity: agent 0 before the step
     const int j = b * PREP_THREADS + tid;
     double sx = 0, sy = 0, qx = 0, qy = 0;
@@ -99,36 +103,17 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a,
         const double ex = x.z - ref.z, ey = x.w - ref.w;
         sx = ex; sy = ey; qx = ex * ex; qy = ey * ey;
     }
-    // stage 1: fixed-shape block reduction
+    // fixed-shape block reduction; the row CTAs add the per-block partials in block order
     __shared__ double red[PREP_THREADS / 32][4];
     sx = warp_sum(sx); sy = warp_sum(sy); qx = warp_sum(qx); qy = warp_sum(qy);
     if ((tid & 31) == 0) { red[tid >> 5][0] = sx; red[tid >> 5][1] = sy; red[tid >> 5][2] = qx; red[tid >> 5][3] = qy; }
     __syncthreads();
-    __shared__ bool last;
     if (tid == 0) {
         double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         for (int w = 0; w < PREP_THREADS / 32; ++w) { t0 += red[w][0]; t1 += red[w][1]; t2 += red[w][2]; t3 += red[w][3]; }
         double *pp = a.partials + ((size_t)env * a.PB + b) * 4;
         pp[0] = t0; pp[1] = t1; pp[2] = t2; pp[3] = t3;
-        __threadfence();
-        last = (atomicAdd(a.counters + env, 1u) == (unsigned)(gridDim.x - 1));
-    }
-    __syncthreads();
-    // stage 2: the last block to arrive adds the partials in block order (deterministic, shard independent)
-    if (last && tid == 0) {
-        __threadfence();
-        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-        const volatile double *pp = a.partials + (size_t)env * a.PB * 4;
-        for (int q = 0; q < (int)gridDim.x; ++q) { t0 += pp[q * 4 + 0]; t1 += pp[q * 4 + 1]; t2 += pp[q * 4 + 2]; t3 += pp[q * 4 + 3]; }
-        double *tt = a.totals + (size_t)env * 8;
-        const double invN = 1.0 / (double)N;
-        const double rew = -((t2 - t0 * t0 * invN) + (t3 - t1 * t1 * invN)) * invN;      // -(var vx + var vy)
-        tt[0] = ref.z; tt[1] = ref.w; tt[2] = t0; tt[3] = t1; tt[4] = rew; tt[5] = ref.x; tt[6] = ref.y;
-        if (a.reward) {
-            if (want_reward_f32) reinterpret_cast<float *>(a.reward)[env] = (float)rew;
-            else reinterpret_cast<double *>(a.reward)[env] = rew;
-        }
-        a.counters[env] = 0u;                                // ready for the next launch
+        if (b == 0) a.needy_cnt[env] = 0u;                   // the kNN fix-up queue of this step starts empty
     }
 }
 
@@ -146,7 +131,7 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a,
 //   overflow  : a (row, lane) list holds SW_LCAP candidates; a row with a fuller list (a swarm far denser than the
 //               reference's) is recomputed by scanning all agents.
 template <typename TO, int LANES, bool KNN>
-__global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
+__global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swarm_kernel(const SArgs a) {
     static_assert(LANES >= 8 && LANES <= 32, "swarm rows are split over 8..32 lanes");
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *tiles = reinterpret_cast<float4 *>(smem + a.off_tiles);          // 2 stages x TS slots
@@ -166,50 +151,68 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     const int ntiles = (NP2 + a.TS - 1) / a.TS;
 
     // ---- setup: barriers; first two tiles in flight ------------------------------------------------------------------
+    double *tot = reinterpret_cast<double *>(smem + a.off_tot);   // (ref vx, ref vy, sum vx, sum vy, -, ref px, ref py, -)
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     fence_async_smem();
-    __syncthreads();
+    pdl_wait();                                                   // the prep kernel's outputs are visible from here on
     auto issue_tile = [&](const int t) {                                     // one thread: queue tile t into stage t&1
         const int s0 = t * a.TS, ns = min(a.TS, NP2 - s0);
         mbar_expect_tx(&bars[t & 1], (unsigned)ns * 16u);
         bulk_load_g2s(tiles + (size_t)(t & 1) * a.TS, pfe + s0, (unsigned)ns * 16u, &bars[t & 1]);
     };
-    if (tid == 0) { issue_tile(0); if (ntiles > 1) issue_tile(1); }
-
-    // ---- zero-fill of the warp's rows of the dense adjacency: plain coalesced 16-byte streaming stores, one slice per
-    //      tile of the main loop, so the writes drain to HBM while the warp filters.  (1-D TMA bulk stores from a shared
-    //      zero block were measured slower, and so is any scheme that writes a sector twice.)
-    float4 *zdst = nullptr;                                  // first 16-byte vector of the warp's region
-    size_t znvec = 0;
-    if (net) {
-        const int wr0 = a.row_lo + blockIdx.x * RTC + ((tid - lane) / LANES) * SW_R;     // first row of this warp
-        const int wr1 = min(min(wr0 + (32 / LANES) * SW_R, a.row_lo + (int)(blockIdx.x + 1) * RTC), a.row_hi);
-        if (wr0 < wr1) {
-            const size_t base = (e0 + wr0) * (size_t)N;
-            const size_t total = (size_t)(wr1 - wr0) * N;
-            constexpr unsigned VEC = 16 / (unsigned)sizeof(TO);
-            const size_t headn = min((size_t)((VEC - (unsigned)(base & (VEC - 1))) & (VEC - 1)), total);
-            znvec = (total - headn) / VEC;
-            TO *out = net + base;
-            if ((size_t)lane < headn) out[lane] = TO(0);
-            if ((size_t)lane < total - (headn + znvec * VEC)) out[headn + znvec * VEC + lane] = TO(0);
-            zdst = reinterpret_cast<float4 *>(out + headn);
+    if (tid < 32) {
+        // warp 0: the env's velocity sums = the prep blocks' partials added in block order (lane-strided, then a fixed
+        // shuffle tree): the same bits in every CTA, on every rank, whatever the shard
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        const double *pp = a.partials + (size_t)env * a.PB * 4;
+        for (int q = lane; q < a.PB; q += 32) {
+            const double2 p01 = *reinterpret_cast<const double2 *>(pp + (size_t)q * 4);
+            const double2 p23 = *reinterpret_cast<const double2 *>(pp + (size_t)q * 4 + 2);
+            t0 += p01.x; t1 += p01.y; t2 += p23.x; t3 += p23.y;
+        }
+        t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2); t3 = warp_sum(t3);
+        if (lane == 0) {
+            const double4 ref = ld_state(a.x_in + e0 * 4);        // origin / reference velocity: agent 0 before the step
+            const double invN = 1.0 / (double)N;
+            const double rew = -((t2 - t0 * t0 * invN) + (t3 - t1 * t1 * invN)) * invN;      // -(var vx + var vy)
+            tot[0] = ref.z; tot[1] = ref.w; tot[2] = t0; tot[3] = t1; tot[4] = rew; tot[5] = ref.x; tot[6] = ref.y;
+            if (a.reward && blockIdx.x == 0) reinterpret_cast<TO *>(a.reward)[env] = (TO)rew;
         }
     }
-    const size_t zper = ((znvec + (size_t)ntiles - 1) / (size_t)ntiles + 255) & ~(size_t)255;   // vectors per tile (x256)
-    auto zero_slice = [&](const int t) {
-        const size_t lo = (size_t)t * zper, hi = min(lo + zper, znvec);
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        size_t v = lo + lane;
-        for (; v + 7 * 32 < hi; v += 8 * 32) {               // 8 stores in flight per lane, 512 contiguous bytes per warp store
+    __syncthreads();                                              // barriers initialised, totals published
+    if (tid == 0) { issue_tile(0); if (ntiles > 1) issue_tile(1); }
+
+    // ---- fill warps: zero the CTA's rows of the dense adjacency (one contiguous run of RTC * N elements) with coalesced
+    //      16-byte streaming stores while the other warps filter; they meet again at the block barrier before the non-zero
+    //      entries are stored.  (A filtering warp that also stores stalls on the store queue; measured 0.27 ms per step.)
+    if (tid >= SW_THREADS) {
+        if (net) {
+            const int r0 = a.row_lo + blockIdx.x * RTC, r1 = min(r0 + RTC, a.row_hi);
+            if (r0 < r1) {
+                const size_t base = (e0 + r0) * (size_t)N;
+                const size_t total = (size_t)(r1 - r0) * N;
+                constexpr unsigned VEC = 16 / (unsigned)sizeof(TO);
+                const size_t headn = min((size_t)((VEC - (unsigned)(base & (VEC - 1))) & (VEC - 1)), total);
+                const size_t nvec = (total - headn) / VEC;
+                TO *out = net + base;
+                const int ft = tid - SW_THREADS, nft = blockDim.x - SW_THREADS;
+                if ((size_t)ft < headn) out[ft] = TO(0);
+                if ((size_t)ft < total - (headn + nvec * VEC)) out[headn + nvec * VEC + ft] = TO(0);
+                float4 *zdst = reinterpret_cast<float4 *>(out + headn);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                size_t v = ft;
+                for (; v + 7 * (size_t)nft < nvec; v += 8 * (size_t)nft) {     // 8 stores in flight per lane
 #pragma unroll
-            for (int q = 0; q < 8; ++q) __stcs(zdst + v + q * 32, z4);
+                    for (int q = 0; q < 8; ++q) __stcs(zdst + v + (size_t)q * nft, z4);
+                }
+                for (; v < nvec; v += nft) __stcs(zdst + v, z4);
+            }
         }
-        for (; v < hi; v += 32) __stcs(zdst + v, z4);
-    };
+        __syncthreads();                                          // (B) the zero stores precede the non-zero stores
+        return;
+    }
 
     // ---- per-row filter state ----------------------------------------------------------------------------------------
-    const double *tot = a.totals + (size_t)env * 8;
     // Flocking-v0: the 7 nearest neighbours are searched among the candidates, so the candidate radius is inflated
     // (x4 in r2: ~36 candidates per row at the reference density); rows that still find fewer than 7 rescan all agents.
     const float tc = (float)a.thrC * (KNN ? 4.0f : 1.0f), rc = sqrtf(tc);
@@ -233,7 +236,6 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
     // ---- stream the tiles: filter only ---------------------------------------------------------------------------------
     for (int t = 0; t < ntiles; ++t) {
         const int s0 = t * a.TS, ns = min(a.TS, NP2 - s0);
-        if (znvec) zero_slice(t);                            // queued before the wait: drains while the tile is filtered
         mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
         const float4 *pe = tiles + (size_t)(t & 1) * a.TS;
         // slots sub, sub+LANES, ... ; bit 2q / 2q+1 of a word = the two agents of the word's q-th slot
@@ -280,9 +282,10 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
                 }
             }
         }
-        __syncthreads();                                     // everyone is done with stage t&1
+        asm volatile("bar.sync 1, %0;" ::"n"(SW_THREADS) : "memory");   // the filtering threads are done with stage t&1
         if (tid == 0 && t + 2 < ntiles) issue_tile(t + 2);
     }
+    __syncthreads();                                         // (B) the fill warps have issued the CTA's zero stores
 
     // ---- refine, row by row (the lists are private to the thread: no barrier needed) ------------------------------------
     const bool cen = a.centralized != 0;
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(256, 2) flock_swarm_kernel(const SArgs a) {
 template <typename TO>
 __global__ void __launch_bounds__(256) flock_knn_fix_kernel(const SArgs a) {
     const int env = blockIdx.y;
+    pdl_wait();
     const unsigned cnt = min(a.needy_cnt[env], (unsigned)NEEDY_CAP);
     __shared__ double sd[8 * TOPK];
     __shared__ int si[8 * TOPK];

@@ -16,15 +16,13 @@ int swarm_go(const flock::SArgs &a, bool knn, dim3 grid, size_t smem, cudaStream
         CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         configured_dev = dev;
     }
-    if (knn) k1<<<grid, 256, smem, st>>>(a); else k0<<<grid, 256, smem, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FLOCK_OK;
+    const dim3 block(flock::SW_THREADS + 32 * a.fill_warps);
+    return knn ? launch_pdl(k1, grid, block, smem, st, true, a) : launch_pdl(k0, grid, block, smem, st, true, a);
 }
 template <typename TO>
 int swarm_all(const flock::SArgs &a, int lanes, bool knn, int PB, dim3 grid, size_t smem, cudaStream_t st) {
-    flock::flock_prep_kernel<<<dim3(PB, a.E), flock::PREP_THREADS, 0, st>>>(a, sizeof(TO) == 4 ? 1 : 0);
-    CUDA_TRY(cudaGetLastError());
-    int rc;
+    int rc = launch_pdl(flock::flock_prep_kernel, dim3(PB, a.E), dim3(flock::PREP_THREADS), 0, st, true, a);
+    if (rc) return rc;
     switch (lanes) {
         case 8: rc = swarm_go<TO, 8>(a, knn, grid, smem, st); break;
         case 16: rc = swarm_go<TO, 16>(a, knn, grid, smem, st); break;
@@ -32,9 +30,7 @@ int swarm_all(const flock::SArgs &a, int lanes, bool knn, int PB, dim3 grid, siz
     }
     if (rc || !knn) return rc;
     // rows whose kNN search found fewer than 7 agents inside the inflated radius: one CTA per row rescans everything
-    flock::flock_knn_fix_kernel<TO><<<dim3(128, a.E), 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FLOCK_OK;
+    return launch_pdl(flock::flock_knn_fix_kernel<TO>, dim3(128, a.E), dim3(256), 0, st, true, a);
 }
 }  // namespace
 
