@@ -44,7 +44,7 @@ class FlockParams(ctypes.Structure):
 class FlockAux(ctypes.Structure):
     """Optional extra outputs of a step (include/flock_b200.h); device pointers, all nullable."""
     _fields_ = [("nonfinite", ctypes.c_void_p), ("adj_bits", ctypes.c_void_p), ("degree", ctypes.c_void_p),
-                ("min_dist", ctypes.c_void_p), ("vel_diff", ctypes.c_void_p)]
+                ("min_dist", ctypes.c_void_p), ("vel_diff", ctypes.c_void_p), ("knn_hint", ctypes.c_void_p)]
 
 
 class FlockError(RuntimeError):

@@ -104,7 +104,9 @@ bool group_layout(const FlockParams *p, int tbytes, bool knn, int G, flock::GArg
     g.off_stats = align16((size_t)g.off_masks + (size_t)flock::GMS * (W + 1) * 4);     // one spare word row (prefetch)
     g.off_idg = g.off_stats + 2 * g.stats_bytes;
     g.off_obs = align16((size_t)g.off_idg + (size_t)threads * 8);
-    smem = (size_t)g.off_obs + (knn ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0);
+    g.off_masks2 = align16((size_t)g.off_obs + (knn ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0));
+    g.off_hint = align16((size_t)g.off_masks2 + (knn ? (size_t)flock::GMS * W * 4 : 0));
+    smem = (size_t)g.off_hint + (knn ? (size_t)threads * 16 : 0);
     g.G = G; g.NP2 = NP2; g.W = W;
     return smem <= kMaxSmem;
 }
@@ -256,7 +258,7 @@ flock::AuxOut aux_out(const FlockAux *aux, int N) {
     o.WB = (N + 31) / 32;
     if (aux) {
         o.nonfinite = aux->nonfinite; o.adj_bits = aux->adj_bits; o.degree = aux->degree;
-        o.min_dist = aux->min_dist; o.vel_diff = aux->vel_diff;
+        o.min_dist = aux->min_dist; o.vel_diff = aux->vel_diff; o.knn_hint = aux->knn_hint;
     }
     return o;
 }
@@ -280,7 +282,7 @@ int check_step_args(const FlockParams *p, const double *x_in, const double *u_in
     if (reward && (reinterpret_cast<uintptr_t>(reward) % sizeof(T)))
         return fail(FLOCK_EALIGN, "reward must be aligned to its element size");
     if (aux && (misaligned(aux->nonfinite, 4) || misaligned(aux->adj_bits, 4) || misaligned(aux->degree, 4) ||
-                misaligned(aux->min_dist, sizeof(T)) || misaligned(aux->vel_diff, sizeof(T))))
+                misaligned(aux->min_dist, sizeof(T)) || misaligned(aux->vel_diff, sizeof(T)) || misaligned(aux->knn_hint, 16)))
         return fail(FLOCK_EALIGN, "FlockAux buffers must be element aligned");
     return FLOCK_OK;
 }
@@ -441,6 +443,7 @@ struct FlockCtx {
     double *u[2];      // u[0]: action to apply (uploaded, or the cached controller action); u[1]: next
     void *values, *network, *reward, *obs;
     void *stat_a, *stat_b;   // get_stats() scratch [E][N]
+    uint16_t *knn_hint;      // [E][N][8] last step's neighbours (search-radius hint of the next kNN)
     int cur;
     int u_cached_flags;   // centralized flag the cached action was computed with; -1 = none
 };
@@ -456,6 +459,12 @@ size_t n_obs(const FlockCtx *c) { return (size_t)c->p.n_envs * c->p.n_agents * 4
 int ctx_run(FlockCtx *c, const double *u_dev, double *x_out, bool want_values, bool want_net, bool want_reward,
             bool want_obs, double *u_next, const FlockAux *aux = nullptr) {
     void *obs = (want_obs && (c->p.flags & FLOCK_KNN_OBS)) ? c->obs : nullptr;
+    FlockAux hint_only;
+    if (!aux && obs && c->knn_hint) {
+        memset(&hint_only, 0, sizeof(hint_only));
+        hint_only.knn_hint = c->knn_hint;
+        aux = &hint_only;
+    }
     if (c->tbytes == 8)
         return step_impl<double>(&c->p, c->x[c->cur], u_dev, x_out, want_values ? (double *)c->values : nullptr,
                                  want_net ? (double *)c->network : nullptr, want_reward ? (double *)c->reward : nullptr,
@@ -605,6 +614,11 @@ int flock_ctx_create(FlockCtx **out, const FlockParams *p, int32_t dtype_bytes, 
     if (e == cudaSuccess) e = cudaMalloc(&c->network, n_net(c) * tb);
     if (e == cudaSuccess) e = cudaMalloc(&c->reward, (size_t)p->n_envs * tb);
     if (e == cudaSuccess) e = cudaMalloc(&c->obs, n_obs(c) * tb);
+    if (e == cudaSuccess && (p->flags & FLOCK_KNN_OBS)) {
+        const size_t hb = (size_t)p->n_envs * p->n_agents * 16;
+        e = cudaMalloc((void **)&c->knn_hint, hb);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->knn_hint, 0, hb, c->stream);
+    }
     if (e != cudaSuccess) {
         flock_ctx_destroy(c);
         return fail(e == cudaErrorMemoryAllocation ? FLOCK_ENOMEM : FLOCK_ECUDA, "ctx_create: %s", cudaGetErrorString(e));
@@ -619,7 +633,7 @@ void flock_ctx_destroy(FlockCtx *c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (int i = 0; i < 2; ++i) { cudaFree(c->x[i]); cudaFree(c->u[i]); }
     cudaFree(c->values); cudaFree(c->network); cudaFree(c->reward); cudaFree(c->obs);
-    cudaFree(c->stat_a); cudaFree(c->stat_b);
+    cudaFree(c->stat_a); cudaFree(c->stat_b); cudaFree(c->knn_hint);
     cudaGetLastError();
     delete c;
 }

@@ -47,6 +47,7 @@ struct AuxOut {               // optional extra outputs (FlockAux of the C ABI);
     int *degree;              // [E][N]
     void *min_dist;           // [E][N] TO  get_stats()['min_dists']   flocking_relative.py:141-142
     void *vel_diff;           // [E][N] TO  get_stats()['vel_diffs']   flocking_relative.py:138-140
+    void *knn_hint;           // [E][N][8] u16 in/out: the row's 7 nearest of the previous step (a search-radius hint only)
     int WB;                   // words per row: ceil(N / 32)
 };
 
@@ -133,7 +134,8 @@ template <typename T> struct TopK {
 // (flocking_relative.py:114), ties to the lower index.  `id` holds TOPK agent indices found with approximate keys (fp32 /
 // fused fp64); the row's own index (the diagonal, or an unused slot) sorts last.  The approximate order is almost always
 // right, so check first and run the insertion network only when some lane of the warp is out of order.
-__device__ __forceinline__ void knn_rerank(const double4 xi, const int i, const double4 *xe, int (&id)[TOPK]) {
+// Returns the exact r2 of the KNN_K-th neighbour (+inf when the row has fewer).
+__device__ __forceinline__ double knn_rerank(const double4 xi, const int i, const double4 *xe, int (&id)[TOPK]) {
     double key[TOPK];
 #pragma unroll
     for (int m = 0; m < TOPK; ++m) {
@@ -157,6 +159,7 @@ __device__ __forceinline__ void knn_rerank(const double4 xi, const int i, const 
             }
         }
     }
+    return key[KNN_K - 1];
 }
 
 // 1/deg in the output type, shared by every kernel so that row shards, lanes and kernels agree bit for bit.

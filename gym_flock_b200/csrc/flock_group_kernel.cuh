@@ -44,6 +44,7 @@ struct GArgs {
     double thrC, R2, Rm, dt, inv_ascale, ulim;
     StepVariant var;
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
+    unsigned off_masks2, off_hint;   // Flocking-v0: kNN candidate mask (same layout as masks), last step's neighbours [T][8] u16
     unsigned xs_bytes, pf_bytes, stats_bytes;    // size of ONE copy of the parity-duplicated arrays
 };
 
@@ -168,6 +169,13 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
     for (int q = tid; q < 2 * genv; q += blockDim.x)       // ready counters of both parities
         reinterpret_cast<double *>(smem + a.off_stats + (q >= genv ? a.stats_bytes : 0u))[(q % genv) * STATS_PER_ENV + 2] = 0.0;
     pdl_wait();                                            // (programmatic dependent launch: the previous step's stores are visible)
+    if constexpr (KNN) {
+        // last step's neighbours, if the caller kept them (FlockAux.knn_hint); else "self": a zero radius -> the first step
+        // searches all N agents
+        uint4 hv = make_uint4((unsigned)i | ((unsigned)i << 16), (unsigned)i | ((unsigned)i << 16), (unsigned)i | ((unsigned)i << 16), (unsigned)i);
+        if (a.aux.knn_hint != nullptr && valid) hv = reinterpret_cast<const uint4 *>(a.aux.knn_hint)[grow];
+        *reinterpret_cast<uint4 *>(smem + a.off_hint + (size_t)tid * 16) = hv;
+    }
     if (valid) {
         double4 x = ld_state(a.x_in + grow * 4);
         const double2 ref = __ldg(reinterpret_cast<const double2 *>(a.x_in + (size_t)env * N * 4));   // env origin: agent 0 before the step
@@ -225,24 +233,25 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
 
         // ---- phase A: filter over all N pairs; candidate bits in shared memory, bit k of the row <-> agent k ------------------
-        int cnt = 0;
-        TopK<TK> top;
-        unsigned kp[TOPK];
-        unsigned kidx = 1;
-        constexpr bool KPACK = KNN && PA32;
-        if constexpr (KPACK) {
-            while ((int)kidx < N) kidx <<= 1;
-            kidx -= 1;
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;
-        } else if constexpr (KNN) {
-            top.init(i);
-        }
-        auto kp_insert = [&](unsigned k) {
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
-        };
+        // Flocking-v0 (KNN): a second mask collects the agents within tau, an UPPER BOUND on the row's 7th-nearest distance
+        // derived from last step's neighbours (the 7 nearest of this step are among the agents at least as close as the
+        // farthest of ANY 7 agents); neighbourhoods change slowly, so that mask holds 7-10 agents instead of N.  The hint
+        // only sets the radius: stale, missing or garbage hints cost time (a mask with < 7 agents falls back to all N),
+        // never correctness.
+        int cnt = 0, cntk = 0;
         int nw;
+        [[maybe_unused]] unsigned *mkrow = reinterpret_cast<unsigned *>(smem + a.off_masks2) + tid;
+        [[maybe_unused]] unsigned short *hint = reinterpret_cast<unsigned short *>(smem + a.off_hint) + tid * 8;
+        [[maybe_unused]] double tau = 0.0;
+        if constexpr (KNN) {
+#pragma unroll
+            for (int m = 0; m < KNN_K; ++m) {
+                const double4 xh = xe[min((int)hint[m], N - 1)];
+                const double dx = xi.x - xh.x, dy = xi.y - xh.y;
+                tau = fmax(tau, fma(dx, dx, dy * dy));
+            }
+            tau *= 1.0 + 1e-12;                              // (covers fused vs unfused rounding of the same distance)
+        }
         if constexpr (PA32) {
             const int nslots = NP2;
             nw = (2 * nslots + 31) >> 5;
@@ -250,87 +259,69 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
             const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
             const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
-            // conservative per-row threshold (covers the fp32 rounding of both positions and of the fused form)
-            const float thrA = fmaf(a.thr_b, fmaxf(fabsf(pxi), fabsf(pyi)) + a.thr_c, a.thr_a);
+            // conservative per-row thresholds (cover the fp32 rounding of both positions and of the fused form)
+            const float pm = fmaxf(fabsf(pxi), fabsf(pyi));
+            const float thrA = fmaf(a.thr_b, pm + a.thr_c, a.thr_a);
             const float2 nthr2 = make_float2(-thrA, -thrA);
-            auto word = [&](const int w, const int tend, const bool full) {
+            [[maybe_unused]] float2 nthrk2 = nthr2;
+            if constexpr (KNN) {
+                const float tk = __double2float_ru(tau), rk = sqrtf(tk);
+                const float thrK = tk * (1.0f + 3e-6f) + 16.0f * rk * (pm + 2.0f * rk) * 5.9604645e-8f;
+                nthrk2 = make_float2(-thrK, -thrK);
+            }
+            // s = dx^2 + (dy^2 - thr): the candidate test is the SIGN of s; one funnel shift per pair moves it into the word
+            // (first pair ends up highest: one BREV per word)
+            auto word = [&](const int w, const int tend, auto FULL) {
                 unsigned bits = 0;
+                [[maybe_unused]] unsigned bitsk = 0;
                 const int tbase = w * 16;
-                if constexpr (KNN) {
-                    auto body = [&](const int tt) {
-                        const float4 q = pe[tbase + tt];
-                        const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
-                        const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
-                        const float2 r2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
-                        bits |= (r2.x < thrA) ? (1u << (2 * tt)) : 0u;
-                        bits |= (r2.y < thrA) ? (2u << (2 * tt)) : 0u;
-                        const unsigned jw = (unsigned)(2 * tbase);
-                        kp_insert(((__float_as_uint(r2.x) & ~kidx) | jw) + (unsigned)(2 * tt));
-                        kp_insert(((__float_as_uint(r2.y) & ~kidx) | jw) + (unsigned)(2 * tt + 1));
-                    };
-                    if (full) {
-#pragma unroll
-                        for (int tt = 0; tt < 16; ++tt) body(tt);
-                    } else {
-                        for (int tt = 0; tt < tend; ++tt) body(tt);
+                auto body = [&](const int tt) {
+                    const float4 q = pe[tbase + tt];
+                    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
+                    const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
+                    const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
+                    bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
+                    bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+                    if constexpr (KNN) {
+                        const float2 sk = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthrk2));
+                        bitsk = __funnelshift_l(__float_as_uint(sk.x), bitsk, 1);
+                        bitsk = __funnelshift_l(__float_as_uint(sk.y), bitsk, 1);
                     }
+                };
+                constexpr int CT = decltype(FULL)::value;        // > 0: compile-time slot count of this word
+                if constexpr (CT > 0) {
+#pragma unroll
+                    for (int tt = 0; tt < CT; ++tt) body(tt);
+                    bits = __brev(bits) >> (32 - 2 * CT);
+                    if constexpr (KNN) bitsk = __brev(bitsk) >> (32 - 2 * CT);
                 } else {
-                    // s = dx^2 + (dy^2 - thrA): the candidate test is the SIGN of s; one funnel shift per pair moves it into
-                    // the word (first pair ends up highest: one BREV per word)
-                    auto body = [&](const int tt) {
-                        const float4 q = pe[tbase + tt];
-                        const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
-                        const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
-                        const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
-                        bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
-                        bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
-                    };
-                    if (full) {
-#pragma unroll
-                        for (int tt = 0; tt < 16; ++tt) body(tt);
-                        bits = __brev(bits);
-                    } else {
-                        for (int tt = 0; tt < tend; ++tt) body(tt);
-                        bits = __brev(bits) >> (32 - 2 * tend);      // 0 < tend < 16
-                    }
+                    for (int tt = 0; tt < tend; ++tt) body(tt);
+                    bits = __brev(bits) >> (32 - 2 * tend);          // 0 < tend <= 16
+                    if constexpr (KNN) bitsk = __brev(bitsk) >> (32 - 2 * tend);
                 }
                 mrow[w * GMS] = bits;
                 cnt += __popc(bits);
+                if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
             };
             if constexpr (NC != 0) {
                 constexpr int NS = (NC + 1) / 2, FW = NS / 16, TAIL = NS - FW * 16;
 #pragma unroll
-                for (int w = 0; w < FW; ++w) word(w, 16, true);
-                if constexpr (TAIL > 0) {
-                    unsigned bits = 0;
-                    if constexpr (!KNN) {
-#pragma unroll
-                        for (int tt = 0; tt < TAIL; ++tt) {
-                            const float4 q = pe[FW * 16 + tt];
-                            const float2 dx = __fadd2_rn(make_float2(q.x, q.y), nx);
-                            const float2 dy = __fadd2_rn(make_float2(q.z, q.w), ny);
-                            const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
-                            bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
-                            bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
-                        }
-                        bits = __brev(bits) >> (32 - 2 * TAIL);
-                        mrow[FW * GMS] = bits;
-                        cnt += __popc(bits);
-                    } else {
-                        word(FW, TAIL, false);
-                    }
-                }
+                for (int w = 0; w < FW; ++w) word(w, 16, std::integral_constant<int, 16>{});
+                if constexpr (TAIL > 0) word(FW, TAIL, std::integral_constant<int, TAIL>{});
             } else {
                 for (int w = 0; w * 16 < nslots; ++w) {
                     const int tend = min(16, nslots - w * 16);
-                    word(w, tend, tend == 16);
+                    if (tend == 16) word(w, 16, std::integral_constant<int, 16>{});
+                    else word(w, tend, std::integral_constant<int, 0>{});
                 }
             }
         } else {
             nw = (N + 31) >> 5;
             const double thrC = a.thrC;
+            [[maybe_unused]] const double thrK = tau;
             for (int w = 0; w * 32 < N; ++w) {
                 unsigned bits = 0;
+                [[maybe_unused]] unsigned bitsk = 0;
                 const int kbase = w * 32;
                 const int kend = min(32, N - kbase);
                 auto body = [&](const int kk) {
@@ -339,7 +330,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
                     const double r2 = fma(dx, dx, dy * dy);
                     bits |= (r2 <= thrC) ? (1u << kk) : 0u;
-                    if constexpr (KNN) top.insert(r2, j);
+                    if constexpr (KNN) bitsk |= (r2 <= thrK) ? (1u << kk) : 0u;
                 };
                 if (kend == 32) {
 #pragma unroll 8
@@ -349,22 +340,76 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 }
                 mrow[w * GMS] = bits;
                 cnt += __popc(bits);
+                if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
             }
         }
 
         // ---- kNN observation: obs[i, 4m:4m+4] = x_i - x_nbr(m), staged per warp and stored coalesced      flocking.py:20-24
         if constexpr (KNN) {
-            int nb[TOPK];
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) {
-                if constexpr (KPACK) {
-                    const int id = (int)(kp[m] & kidx);
-                    nb[m] = (id < N) ? id : i;               // (odd N: the pad slot at +inf is not an agent)
-                } else {
-                    nb[m] = top.id[m];
-                }
+            constexpr bool KPACK = PA32;
+            // Selection keys.  fp32 mode: the fp32 bits of r2 (non-negative, so they order as unsigned integers) with the low
+            // ceil(log2 N) mantissa bits replaced by the agent index -- a branch-free min/max network; fp64 mode: fused fp64 r2.
+            // Both keep TOPK = 9 survivors (the row itself + 7 + one slack slot); knn_rerank orders them exactly.
+            TopK<double> top;
+            unsigned kp[TOPK];
+            unsigned kidx = 1;
+            if constexpr (KPACK) {
+                while ((int)kidx < N) kidx <<= 1;
+                kidx -= 1;
             }
-            knn_rerank(xi, i, xe, nb);
+            auto consider = [&](const int j) {
+                if constexpr (KPACK) {
+                    const float *pj = reinterpret_cast<const float *>(pf + g * NP2 + (j >> 1));
+                    const float *pif = reinterpret_cast<const float *>(pf + g * NP2 + (i >> 1));
+                    const float dx = pj[j & 1] - pif[i & 1], dy = pj[2 + (j & 1)] - pif[2 + (i & 1)];
+                    unsigned k = (__float_as_uint(fmaf(dx, dx, dy * dy)) & ~kidx) | (unsigned)j;
+#pragma unroll
+                    for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
+                } else {
+                    const double4 xj = xe[j];
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    top.insert(fma(dx, dx, dy * dy), j);
+                }
+            };
+            // The mask holds every agent with r2 <= tau (the filter has no false negatives).  If the 7th neighbour found in it is
+            // itself within tau, no agent outside the mask can be closer: done.  Otherwise (no usable hint: first step,
+            // teleported agents, N <= 8) the warp searches all N agents.
+            int nb[TOPK];
+            bool use_mask = __all_sync(__activemask(), !valid || cntk >= KNN_K + 1) && N > KNN_K + 1;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if constexpr (KPACK) {
+#pragma unroll
+                    for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;
+                } else {
+                    top.init(i);
+                }
+                if (use_mask) {
+                    for (int w = 0; w < nw; ++w) {
+                        unsigned b = mkrow[w * GMS];
+                        while (b) { const int j = w * 32 + __ffs(b) - 1; b &= b - 1; if (j < N) consider(j); }
+                    }
+                } else {
+                    for (int j = 0; j < N; ++j) consider(j);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < TOPK; ++m) {
+                    if constexpr (KPACK) nb[m] = (int)(kp[m] & kidx);
+                    else nb[m] = top.id[m];
+                }
+                const double key7 = knn_rerank(xi, i, xe, nb);
+                if (!use_mask || __all_sync(__activemask(), !valid || key7 <= tau)) break;
+                use_mask = false;
+            }
+#pragma unroll
+            for (int m = 0; m < KNN_K; ++m) hint[m] = (unsigned short)nb[m];           // next step's radius comes from these
+            if (a.aux.knn_hint != nullptr && last_step && valid) {
+                uint4 hv;
+                hv.x = (unsigned)nb[0] | ((unsigned)nb[1] << 16); hv.y = (unsigned)nb[2] | ((unsigned)nb[3] << 16);
+                hv.z = (unsigned)nb[4] | ((unsigned)nb[5] << 16); hv.w = (unsigned)nb[6];
+                reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
+            }
             if (a.obs) {
                 TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
                 TO *o = obs_w + lane * (NXS * KNN_K);

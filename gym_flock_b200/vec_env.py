@@ -73,9 +73,12 @@ class FlockVecEnv:
         self.words = int(self.lib.flock_adj_words(N))
         self.adj_bits = torch.zeros(E, N, self.words, dtype=torch.int32, device=dev) if adjacency_mode == "bitmask" else None
         self.degree = torch.zeros(E, N, dtype=torch.int32, device=dev) if adjacency_mode == "bitmask" else None
+        # Flocking-v0: last step's 7 nearest per row -- only a search-radius hint for the next step's kNN (never affects results)
+        self._knn_hint = torch.zeros(E, N, 8, dtype=torch.int16, device=dev) if self.knn else None
         self._aux = _lib.FlockAux(self.nonfinite.data_ptr(),
                                   self.adj_bits.data_ptr() if self.adj_bits is not None else None,
-                                  self.degree.data_ptr() if self.degree is not None else None, None, None)
+                                  self.degree.data_ptr() if self.degree is not None else None, None, None,
+                                  self._knn_hint.data_ptr() if self._knn_hint is not None else None)
         self.elapsed = 0
         self._fn_step = self.lib.flock_step_aux_f64 if self.dtype == torch.float64 else self.lib.flock_step_aux_f32
         self._fn_roll = self.lib.flock_rollout_f64 if self.dtype == torch.float64 else self.lib.flock_rollout_f32
@@ -111,7 +114,7 @@ class FlockVecEnv:
 
     def _launch(self, x_in, u_in, x_out, u_next, want_obs=True, aux=None):
         if aux is None:
-            aux = self._aux if want_obs else _lib.FlockAux(self.nonfinite.data_ptr(), None, None, None, None)
+            aux = self._aux if want_obs else _lib.FlockAux(self.nonfinite.data_ptr(), None, None, None, None, None)
         with torch.cuda.device(self.device):
             _lib.check(self._fn_step(self._pp, self._ptr(x_in), self._ptr(u_in), self._ptr(x_out),
                                      self._ptr(self.values) if want_obs else None,
@@ -220,7 +223,7 @@ class FlockVecEnv:
         {'vel_diffs': [E,N], 'min_dists': [E,N]} in the observation dtype."""
         vd = torch.empty(self.E, self.N, dtype=self.dtype, device=self.device)
         md = torch.empty(self.E, self.N, dtype=self.dtype, device=self.device)
-        aux = _lib.FlockAux(None, None, None, md.data_ptr(), vd.data_ptr())
+        aux = _lib.FlockAux(None, None, None, md.data_ptr(), vd.data_ptr(), None)
         with torch.cuda.device(self.device):
             _lib.check(self._fn_step(self._pp, self._ptr(self.x), None, None, None, None, None, None, None,
                                      ctypes.byref(aux), self._stream()))

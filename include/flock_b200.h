@@ -116,6 +116,12 @@ typedef struct FlockAux {
     int32_t  *degree;       /* [E][N]  neighbours per row (the divisor of adj_mean, before the 0 -> 1 fix, :120-121) */
     void     *min_dist;     /* [E][N]  get_stats()['min_dists']: min_j sqrt(r2[i][j]) (:141-142) */
     void     *vel_diff;     /* [E][N]  get_stats()['vel_diffs']: |v_i - mean_j v_j| (:138-140) */
+    uint16_t *knn_hint;     /* [E][N][8] in/out, 16-byte aligned; FLOCK_KNN_OBS only.  The 7 nearest neighbours of each row at
+                             *      the previous step (slot 7 unused).  Read before the step as a SEARCH-RADIUS hint -- the 7
+                             *      nearest now are among the agents at least as close as the farthest of any 7 agents -- and
+                             *      rewritten with this step's neighbours.  Contents never affect results, only speed: zeros,
+                             *      stale or arbitrary values make the row search all agents.  Batched path (one thread per
+                             *      row, n_agents <= 512) only; ignored elsewhere. */
 } FlockAux;
 
 /* words per row of FlockAux.adj_bits: ceil(n_agents / 32) */

@@ -40,11 +40,11 @@ def test_params_struct_layout_matches_header():
 
 def test_aux_struct_layout_and_validation(L):
     from gym_flock_b200 import _lib
-    assert ctypes.sizeof(_lib.FlockAux) == 40 and _lib.FlockAux.vel_diff.offset == 32
+    assert ctypes.sizeof(_lib.FlockAux) == 48 and _lib.FlockAux.vel_diff.offset == 32 and _lib.FlockAux.knn_hint.offset == 40
     assert L.flock_adj_words(100) == 4 and L.flock_adj_words(32) == 1 and L.flock_adj_words(33) == 2
     buf = np.zeros(64, dtype=np.float64)
     ptr = ctypes.c_void_p((buf.ctypes.data + 15) & ~15)
-    aux = _lib.FlockAux(ptr.value + 2, None, None, None, None)                 # misaligned int32 flag buffer
+    aux = _lib.FlockAux(ptr.value + 2, None, None, None, None, None)           # misaligned int32 flag buffer
     p = _lib.make_params(1, 4)
     assert L.flock_step_aux_f64(ctypes.byref(p), ptr, None, None, None, None, None, None, None, ctypes.byref(aux), None) == -2
     assert p.reserved == 0                                                      # bindings never set the diagnostics word
