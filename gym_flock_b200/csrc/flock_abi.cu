@@ -346,9 +346,9 @@ int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, doub
 }
 
 // ---- large swarms: prep kernel + streaming row kernel (flock_swarm_kernel.cuh) --------------------------------------
-struct SwarmLayout { size_t off_pf, off_partials, off_needy_cnt, off_needy, bytes; int NP2, PB; };
+struct SwarmLayout { size_t off_pf, off_partials, off_needy_cnt, off_needy, off_ovf, bytes; int NP2, PB; };
 
-SwarmLayout swarm_layout(int E, int N) {
+SwarmLayout swarm_layout(int E, int N, int nrows) {
     SwarmLayout L;
     L.NP2 = (N + 1) / 2;
     L.PB = (N + flock::PREP_THREADS - 1) / flock::PREP_THREADS;
@@ -356,7 +356,8 @@ SwarmLayout swarm_layout(int E, int N) {
     L.off_partials = ((size_t)E * L.NP2 * 16 + 255) & ~(size_t)255;
     L.off_needy_cnt = L.off_partials + (((size_t)E * L.PB * 32 + 255) & ~(size_t)255);
     L.off_needy = L.off_needy_cnt + (((size_t)E * 4 + 255) & ~(size_t)255);
-    L.bytes = L.off_needy + (size_t)E * flock::NEEDY_CAP * 4;
+    L.off_ovf = L.off_needy + (((size_t)E * flock::NEEDY_CAP * 4 + 255) & ~(size_t)255);
+    L.bytes = L.off_ovf + (size_t)E * nrows * 32 * flock::SW_LCAP2 * 4;       // second tier of the candidate lists
     return L;
 }
 
@@ -378,7 +379,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     if (misaligned(x_in) || misaligned(u_in) || misaligned(x_out) || misaligned(values, std::min<uintptr_t>(16, 2 * sizeof(T))) ||
         misaligned(network, sizeof(T)) || misaligned(u_next) || misaligned(obs) || (reinterpret_cast<uintptr_t>(scratch) & 255u))
         return fail(FLOCK_EALIGN, "device buffers must be 16-byte aligned (values: 8, network: element size, scratch: 256)");
-    const SwarmLayout L = swarm_layout(E, N);
+    const SwarmLayout L = swarm_layout(E, N, row_hi - row_lo);
     if (scratch_bytes < L.bytes) return fail(FLOCK_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, L.bytes);
     int lanes = p->lanes > 0 ? p->lanes : 32;
     if (lanes != 8 && lanes != 16 && lanes != 32) return fail(FLOCK_EINVAL, "swarm path: lanes must be 8, 16 or 32");
@@ -393,6 +394,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.partials = reinterpret_cast<double *>(sc + L.off_partials);
     a.needy_cnt = reinterpret_cast<unsigned *>(sc + L.off_needy_cnt);
     a.needy_rows = reinterpret_cast<unsigned *>(sc + L.off_needy);
+    a.ovf = reinterpret_cast<unsigned *>(sc + L.off_ovf);
     a.E = E; a.N = N; a.NP2 = L.NP2; a.PB = L.PB; a.row_lo = row_lo; a.row_hi = row_hi;
     a.RT = flock::SW_R * (256 / lanes);        // rows per CTA
     a.TS = 2048;
@@ -549,7 +551,10 @@ int flock_reset_sample(const FlockParams *p, double r_max, double v_max, double 
 
 size_t flock_swarm_scratch_bytes(const FlockParams *p) {
     if (!p || p->n_envs < 1 || p->n_agents < 1) return 0;
-    return swarm_layout(p->n_envs, p->n_agents).bytes;
+    int lo = p->row_lo, hi = p->row_hi;
+    if (lo == 0 && hi == 0) hi = p->n_agents;
+    if (lo < 0 || hi > p->n_agents || lo >= hi) return 0;
+    return swarm_layout(p->n_envs, p->n_agents, hi - lo).bytes;
 }
 int flock_swarm_step_f64(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, double *values,
                          double *network, double *reward, double *u_next, double *obs, void *scratch,

@@ -36,6 +36,7 @@ struct SArgs {
     double *partials;       // scratch: [E][PB][4]  per prep block: sum (v - ref), sum (v - ref)^2
     unsigned *needy_cnt;    // scratch: [E] rows whose kNN search needs a full rescan (cleared by the prep kernel)
     unsigned *needy_rows;   // scratch: [E][NEEDY_CAP]
+    unsigned *ovf;          // scratch: [E][rows][32][SW_LCAP2] second tier of the candidate lists (touched only on overflow)
     int E, N, NP2, PB;
     int row_lo, row_hi;
     int RT;                 // rows per CTA (SW_R * 256 / LANES)
@@ -50,7 +51,8 @@ struct SArgs {
 constexpr int PREP_THREADS = 256;
 constexpr int NEEDY_CAP = 8192;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
 constexpr int SW_R = 2;         // rows per thread in the filter
-constexpr int SW_LCAP = 16;     // candidates per (row, lane)
+constexpr int SW_LCAP = 16;     // candidates per (row, lane) in shared memory ...
+constexpr int SW_LCAP2 = 112;   // ... and in the global second tier (dense swarms): 128 per (row, lane) before the full rescan
 constexpr int SW_THREADS = 256; // filtering threads per CTA (fill warps come on top)
 constexpr int SW_FILL_WARPS = 2;
 }  // namespace flock
@@ -128,8 +130,9 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a)
 //   refine    : after the last tile each thread refines the candidates of its lists in fp64 (x_j through L2), row by
 //               row; the LANES partial sums of a row are combined with xor shuffles.  Per-lane ascending j plus a fixed
 //               shuffle pattern: the result does not depend on how rows are sharded over CTAs or GPUs.
-//   overflow  : a (row, lane) list holds SW_LCAP candidates; a row with a fuller list (a swarm far denser than the
-//               reference's) is recomputed by scanning all agents.
+//   overflow  : a (row, lane) list holds SW_LCAP candidates in shared memory and spills into a second tier of SW_LCAP2 in
+//               global scratch (a swarm several times denser than the reference's: same code path, a few extra L2 accesses);
+//               only a row with more than SW_LCAP + SW_LCAP2 candidates on one lane is recomputed by scanning all agents.
 template <typename TO, int LANES, bool KNN>
 __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swarm_kernel(const SArgs a) {
     static_assert(LANES >= 8 && LANES <= 32, "swarm rows are split over 8..32 lanes");
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
     bool valid[SW_R];
     float2 nx[SW_R], ny[SW_R], nthr[SW_R];
     int cn[SW_R];                                            // candidates of this thread per row (may exceed SW_LCAP)
-    unsigned *lst[SW_R];
+    unsigned *lst[SW_R], *ovl[SW_R];
 #pragma unroll
     for (int r = 0; r < SW_R; ++r) {
         const int i = ibase + r;
@@ -231,6 +234,8 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
         nthr[r] = make_float2(-thrA, -thrA);
         cn[r] = 0;
         lst[r] = lists + ((size_t)tid * SW_R + r) * SW_LCAP;
+        // second tier: [env][row - row_lo][32 lanes][SW_LCAP2]
+        ovl[r] = a.ovf + ((((size_t)env * (a.row_hi - a.row_lo) + (size_t)(valid[r] ? i - a.row_lo : 0)) * 32 + sub) * SW_LCAP2);
     }
 
     // ---- stream the tiles: filter only ---------------------------------------------------------------------------------
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
                     const int j = 2 * (s0 + sub + LANES * (qb + (k >> 1))) + (k & 1);
                     if (j == ibase + r || j >= N) continue;
                     if (cn[r] < SW_LCAP) lst[r][cn[r]] = (unsigned)j;
+                    else if (cn[r] < SW_LCAP + SW_LCAP2) ovl[r][cn[r] - SW_LCAP] = (unsigned)j;
                     ++cn[r];
                 }
             }
@@ -300,19 +306,20 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
         if constexpr (KNN) top.init(i);
         int deg = 0;
         // a list that overflowed anywhere in the row: the whole row is recomputed from all agents (same on every lane)
-        bool over = valid[r] && cn[r] > SW_LCAP;
+        bool over = valid[r] && cn[r] > SW_LCAP + SW_LCAP2;
 #pragma unroll
         for (int m = LANES / 2; m > 0; m >>= 1) over |= (__shfl_xor_sync(0xffffffffu, over ? 1 : 0, m) != 0);
-        const int ncand = valid[r] ? min(cn[r], SW_LCAP) : 0;
+        const int ncand = valid[r] ? min(cn[r], SW_LCAP + SW_LCAP2) : 0;
+        auto slot = [&](const int c) -> unsigned * { return c < SW_LCAP ? lst[r] + c : ovl[r] + (c - SW_LCAP); };
         if (!over) {
             for (int c = 0; c < ncand; ++c) {
-                const int j = (int)lst[r][c];
+                const int j = (int)*slot(c);
                 const double4 xj = ld_state(xc + (size_t)j * 4);
                 if constexpr (KNN) {
                     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
                     top.insert(fma(dx, dx, dy * dy), j);
                 }
-                if (refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) { lst[r][c] = (unsigned)j | 0x80000000u; ++deg; }
+                if (refine_fast<sizeof(TO) == 4>(xi, xj, a.R2, a.Rm, A)) { *slot(c) = (unsigned)j | 0x80000000u; ++deg; }
             }
         } else if (valid[r]) {
             for (int j = sub; j < N; j += LANES) {
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
                 TO *orow = net + grow * N;
                 if (!over) {
                     for (int c = 0; c < ncand; ++c) {
-                        const unsigned e = lst[r][c];
+                        const unsigned e = *slot(c);
                         if (e & 0x80000000u) orow[e & 0x7fffffffu] = idg;
                     }
                 } else {                                     // rare: recompute the row's adjacency

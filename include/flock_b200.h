@@ -180,7 +180,8 @@ int flock_rollout_f32(const FlockParams *p, int32_t steps, double *x_a, double *
 
 /* Large swarms (N beyond what one CTA can stage, e.g. 65 536 agents): same semantics as flock_step_* (x_out is
  * required), computed by an O(N) preparation kernel plus a row kernel that streams all agents' positions through
- * shared memory with TMA bulk loads.  `scratch` is caller-owned device memory of flock_swarm_scratch_bytes(p) bytes,
+ * shared memory with TMA bulk loads.  `scratch` is caller-owned device memory of flock_swarm_scratch_bytes(p) bytes
+ * (p with the row range of the call: the second tier of the per-row candidate lists scales with the rows computed),
  * 256-byte aligned; its contents need not survive between calls.  FLOCK_EXACT_ORDER is not offered here;
  * lanes must be 8, 16 or 32 (0 = 32; use the same value on every rank for shard-independent bits).
  * Replaces the same reference lines as flock_step_* for a single giant swarm (BASELINE config 5). */

@@ -122,22 +122,21 @@ def test_streaming_swarm_sparse_rows_use_knn_fixup(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_streaming_swarm_dense_rows_overflow_the_candidate_lists(precision):
-    """A swarm far denser than the reference's (every row has more candidates inside the inflated radius than its
-    per-lane lists hold): the row kernel's full-scan fallback runs for every row.  Same parity bars as everywhere else."""
+@pytest.mark.parametrize("n,density,min_dist,floor", [(800, 177.0, 0.05, 16 * 32), (4300, 1690.0, 0.008, 128 * 32)])
+def test_streaming_swarm_dense_rows_overflow_the_candidate_lists(precision, n, density, min_dist, floor):
+    """Swarms far denser than the reference's.  (800 agents in a disk of radius 1.2) every row has more candidates inside the
+    inflated radius than the shared-memory lists hold: they spill into the second tier in global scratch.  (4300 agents in a
+    disk of radius 0.9) every lane's list overflows both tiers: the row kernel's full-scan fallback.  Same parity bars."""
     import torch
     from gym_flock_b200 import SwarmEnv
     from gym_flock_b200.synthetic import initial_state
-    from parity_util import check_pass
-    from oracle import c_oracle
-    n = 800
-    x0 = initial_state(n, seed=800, law="density", density=177.0, min_dist=0.05)      # disk of radius 1.2
+    from parity_util import check_knn_obs, check_pass
+    x0 = initial_state(n, seed=n, law="density", density=density, min_dist=min_dist)
     d = x0[:, None, :2] - x0[None, :, :2]
     r2 = (d * d).sum(-1)
-    assert ((r2 <= 3.6).sum(1) - 1).min() > 16 * 32       # more candidates per row than 32 lanes x 16 entries
+    assert ((r2 <= 3.6).sum(1) - 1).min() > floor
     sw = SwarmEnv("Flocking-v0", n_agents=n, precision=precision, streaming=True)
     obs, net = sw.reset(x0)
     torch.cuda.synchronize()
     check_pass(x0, sw.values.cpu().numpy(), net.cpu().numpy(), sw.u.cpu().numpy(), float(sw.reward), precision)
-    from parity_util import check_knn_obs
     check_knn_obs(obs.cpu().numpy(), x0, precision, select_kind="fp64")
