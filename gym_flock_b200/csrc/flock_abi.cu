@@ -57,6 +57,7 @@ inline int tune_group(const FlockParams *p) { return (p->reserved >> 16) & 0xff;
 inline bool tune_no_group(const FlockParams *p) { return (p->reserved >> 24) & 1; }
 inline bool tune_no_pdl(const FlockParams *p) { return (p->reserved >> 25) & 1; }
 inline bool tune_no_fuse(const FlockParams *p) { return (p->reserved >> 26) & 1; }
+inline bool tune_obs_staged(const FlockParams *p) { return (p->reserved >> 27) & 1; }   // bit 27: stage the kNN rows in smem
 
 struct Plan {
     bool group;               // flock_group_kernel (whole envs per CTA) instead of flock_env_kernel
@@ -90,22 +91,25 @@ int validate(const FlockParams *p, int tbytes, int &row_lo, int &row_hi) {
 // (full waves) * occ * T + ceil(rest / 148) * T over the G that fit, preferring fuller CTAs on ties.
 bool group_layout(const FlockParams *p, int tbytes, bool knn, int G, flock::GArgs &g, int &threads, size_t &smem) {
     const int N = p->n_agents;
+    const bool obs_staged = knn && tune_obs_staged(p);
     const bool pa32 = (tbytes == 4);
     const int NP2 = (N + 1) / 2;
     const int W = pa32 ? (2 * NP2 + 31) / 32 : (N + 31) / 32;
     threads = round_up32(G * N);
     if (threads > flock::GMAXT) return false;
+    const int GMS = threads <= 256 ? 256 : 512;        // mask stride of the instantiation launch_group picks
     g.xs_bytes = align16((size_t)G * N * 32);
     g.pf_bytes = pa32 ? align16((size_t)G * NP2 * 16) : 0;
     g.stats_bytes = align16((size_t)G * flock::STATS_PER_ENV * 8);
     g.off_xs = 0;
     g.off_pf = g.off_xs + 2 * g.xs_bytes;
     g.off_masks = g.off_pf + 2 * g.pf_bytes;
-    g.off_stats = align16((size_t)g.off_masks + (size_t)flock::GMS * (W + 1) * 4);     // one spare word row (prefetch)
+    g.off_stats = align16((size_t)g.off_masks + (size_t)GMS * (W + 1) * 4);     // one spare word row (prefetch)
     g.off_idg = g.off_stats + 2 * g.stats_bytes;
     g.off_obs = align16((size_t)g.off_idg + (size_t)threads * 8);
-    g.off_masks2 = align16((size_t)g.off_obs + (knn ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0));
-    g.off_hint = align16((size_t)g.off_masks2 + (knn ? (size_t)flock::GMS * W * 4 : 0));
+    g.off_masks2 = align16((size_t)g.off_obs + (obs_staged ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0));
+    g.off_hint = align16((size_t)g.off_masks2 + (knn ? (size_t)GMS * W * 4 : 0));
+    g.obs_direct = obs_staged ? 0 : 1;
     smem = (size_t)g.off_hint + (knn ? (size_t)threads * 16 : 0);
     g.G = G; g.NP2 = NP2; g.W = W;
     return smem <= kMaxSmem;

@@ -46,9 +46,12 @@ struct GArgs {
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
     unsigned off_masks2, off_hint;   // Flocking-v0: kNN candidate mask (same layout as masks), last step's neighbours [T][8] u16
     unsigned xs_bytes, pf_bytes, stats_bytes;    // size of ONE copy of the parity-duplicated arrays
+    int obs_direct;           // Flocking-v0: every lane stores its own observation row (7 x 16 bytes) instead of staging the
+                              // warp's rows in shared memory for a fully coalesced copy (no staging area: more CTAs per SM)
 };
 
-constexpr int GMS = 512;      // mask words are word-major with this fixed stride (immediate offsets everywhere)
+// mask words are word-major with a fixed stride GMS (immediate offsets everywhere): a template parameter, 256 for CTAs of up
+// to 256 threads, else 512
 constexpr int GMAXT = 512;
 
 // ---- in-warp expansion of 32 consecutive rows of adj_mean, N a compile-time constant ---------------------------------
@@ -99,7 +102,7 @@ __device__ __forceinline__ void expand_rows_const(TO *wout, const unsigned *wm, 
 }
 
 // generic N: flock_env_kernel's expand_rows with this kernel's mask stride
-template <typename TO, int V>
+template <typename TO, int V, int GMS>
 __device__ __forceinline__ void expand_rows_g(TO *wout, const unsigned *wm, const TO *idgs, const int N, const int nrows,
                                               const int lane) {
     const int nv = N / V;
@@ -138,7 +141,7 @@ __device__ __forceinline__ void expand_rows_g(TO *wout, const unsigned *wm, cons
     }
 }
 
-template <typename TO, bool KNN, int NC>
+template <typename TO, bool KNN, int NC, int GMS>
 __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
     constexpr bool PA32 = std::is_same<TO, float>::value;
     using TK = typename std::conditional<PA32, float, double>::type;
@@ -410,7 +413,22 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 hv.z = (unsigned)nb[4] | ((unsigned)nb[5] << 16); hv.w = (unsigned)nb[6];
                 reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
             }
-            if (a.obs) {
+            if (a.obs && a.obs_direct) {
+                if (valid) {
+                    TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
+#pragma unroll
+                    for (int m = 0; m < KNN_K; ++m) {
+                        const double4 xn = xe[nb[m]];
+                        if constexpr (PA32) {
+                            __stcs(reinterpret_cast<float4 *>(o) + m, make_float4((float)(xi.x - xn.x), (float)(xi.y - xn.y),
+                                                                                  (float)(xi.z - xn.z), (float)(xi.w - xn.w)));
+                        } else {
+                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m, make_double2(xi.x - xn.x, xi.y - xn.y));
+                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m + 1, make_double2(xi.z - xn.z, xi.w - xn.w));
+                        }
+                    }
+                }
+            } else if (a.obs) {
                 TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
                 TO *o = obs_w + lane * (NXS * KNN_K);
 #pragma unroll
@@ -568,9 +586,9 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     expand_rows_const<TO, NC, GMS>(wout, wm, idgs, nrw, lane);
                 } else {
                     constexpr int VMAX = 16 / (int)sizeof(TO);
-                    if (N % VMAX == 0) expand_rows_g<TO, VMAX>(wout, wm, idgs, N, nrw, lane);
-                    else if (VMAX == 4 && N % 2 == 0) expand_rows_g<TO, 2>(wout, wm, idgs, N, nrw, lane);
-                    else expand_rows_g<TO, 1>(wout, wm, idgs, N, nrw, lane);
+                    if (N % VMAX == 0) expand_rows_g<TO, VMAX, GMS>(wout, wm, idgs, N, nrw, lane);
+                    else if (VMAX == 4 && N % 2 == 0) expand_rows_g<TO, 2, GMS>(wout, wm, idgs, N, nrw, lane);
+                    else expand_rows_g<TO, 1, GMS>(wout, wm, idgs, N, nrw, lane);
                 }
             }
             __syncwarp();                                    // the next step rewrites the words

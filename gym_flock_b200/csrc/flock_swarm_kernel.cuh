@@ -291,10 +291,11 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
         asm volatile("bar.sync 1, %0;" ::"n"(SW_THREADS) : "memory");   // the filtering threads are done with stage t&1
         if (tid == 0 && t + 2 < ntiles) issue_tile(t + 2);
     }
-    __syncthreads();                                         // (B) the fill warps have issued the CTA's zero stores
 
     // ---- refine, row by row (the lists are private to the thread: no barrier needed) ------------------------------------
     const bool cen = a.centralized != 0;
+    TO idgs[SW_R];
+    bool overs[SW_R];
 #pragma unroll 1
     for (int r = 0; r < SW_R; ++r) {
         const int i = valid[r] ? ibase + r : a.row_lo;
@@ -421,23 +422,32 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
             }
         }
 
-        // ---- the non-zero adj_mean entries, over the warp's zero-filled rows -----------------------------------------------
-        if (net != nullptr) {
-            __syncwarp();                                    // the warp's zero stores precede its non-zero stores
-            if (valid[r]) {
-                TO *orow = net + grow * N;
-                if (!over) {
-                    for (int c = 0; c < ncand; ++c) {
-                        const unsigned e = *slot(c);
-                        if (e & 0x80000000u) orow[e & 0x7fffffffu] = idg;
-                    }
-                } else {                                     // rare: recompute the row's adjacency
-                    for (int j = sub; j < N; j += LANES) {
-                        if (j == i) continue;
-                        const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
-                        const double dx = xi.x - pj.x, dy = xi.y - pj.y;
-                        if (fma(dx, dx, dy * dy) < a.R2) orow[j] = idg;
-                    }
+        idgs[r] = idg; overs[r] = over;
+    }
+
+    // ---- the non-zero adj_mean entries, stored over the zero-filled rows: only this waits for the fill warps (everything
+    //      above -- filter, refine, features, actions, observations -- overlapped with the fill) --------------------------------
+    __syncthreads();                                         // (B) the fill warps have issued the CTA's zero stores
+    if (net != nullptr) {
+#pragma unroll 1
+        for (int r = 0; r < SW_R; ++r) {
+            if (!valid[r]) continue;
+            const int i = ibase + r;
+            TO *orow = net + (e0 + i) * (size_t)N;
+            const TO idg = idgs[r];
+            if (!overs[r]) {
+                const int ncand = min(cn[r], SW_LCAP + SW_LCAP2);
+                for (int c = 0; c < ncand; ++c) {
+                    const unsigned e = c < SW_LCAP ? lst[r][c] : ovl[r][c - SW_LCAP];
+                    if (e & 0x80000000u) orow[e & 0x7fffffffu] = idg;
+                }
+            } else {                                         // rare: recompute the row's adjacency
+                const double2 pi_ = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)i * 4));
+                for (int j = sub; j < N; j += LANES) {
+                    if (j == i) continue;
+                    const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
+                    const double dx = pi_.x - pj.x, dy = pi_.y - pj.y;
+                    if (fma(dx, dx, dy * dy) < a.R2) orow[j] = idg;
                 }
             }
         }

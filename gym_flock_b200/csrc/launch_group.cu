@@ -4,9 +4,9 @@
 #include "flock_group_kernel.cuh"
 
 namespace {
-template <typename TO, bool KNN, int NC>
-int go(const flock::GArgs &g, int grid, int threads, size_t smem, cudaStream_t st, bool pdl) {
-    auto kern = flock::flock_group_kernel<TO, KNN, NC>;
+template <typename TO, bool KNN, int NC, int GMS>
+int go2(const flock::GArgs &g, int grid, int threads, size_t smem, cudaStream_t st, bool pdl) {
+    auto kern = flock::flock_group_kernel<TO, KNN, NC, GMS>;
     static thread_local int configured_dev = -1;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -15,6 +15,11 @@ int go(const flock::GArgs &g, int grid, int threads, size_t smem, cudaStream_t s
         configured_dev = dev;
     }
     return launch_pdl(kern, dim3(grid), dim3(threads), smem, st, pdl, g);
+}
+template <typename TO, bool KNN, int NC>
+int go(const flock::GArgs &g, int grid, int threads, size_t smem, cudaStream_t st, bool pdl) {
+    // mask stride: 256 for CTAs of up to 256 threads (less shared memory, more CTAs per SM), else 512
+    return threads <= 256 ? go2<TO, KNN, NC, 256>(g, grid, threads, smem, st, pdl) : go2<TO, KNN, NC, 512>(g, grid, threads, smem, st, pdl);
 }
 template <typename TO, bool KNN>
 int by_n(const flock::GArgs &g, int grid, int threads, size_t smem, cudaStream_t st, bool pdl) {
