@@ -503,6 +503,48 @@ def measure_e2e(D, cfg, rank, world, Ke):
             "api": "HostFlockBatch.controller()+step(u): NumPy in/out through flock_ctx_* (C ABI)"}
 
 
+def measure_e2e_bitmask(D, cfg, rank, world, Ke):
+    """The same loop with the adjacency as BITS (FlockVecEnv adjacency_mode='bitmask': FlockAux.adj_bits + degree instead of
+    the dense [E,N,N] network), pinned host buffers, copies inside the timed region.  A SEPARATE line: a consumer that
+    aggregates on the graph (flock_aggregate_*) needs no dense matrix; the headline e2e keeps the reference's dense layout."""
+    torch = D.torch
+    from gym_flock_b200 import FlockVecEnv
+    from gym_flock_b200.synthetic import initial_states_fast
+    E, N, prec = envs_per_gpu(cfg, world), cfg["N"], cfg["precision"]
+    x0 = initial_states_fast(E, N, seed=1234 + rank * E)
+    env = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=D.device, adjacency_mode="bitmask")
+    env.reset(x0)
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    u_h, v_h, b_h, d_h, r_h = pin(env.u_cached), pin(env.values), pin(env.adj_bits), pin(env.degree), pin(env.reward)
+    o_h = pin(env.obs) if env.obs is not None else None
+
+    def one():
+        u_h.copy_(env.controller(), non_blocking=True)            # D2H  u[E,N,2]
+        torch.cuda.synchronize()
+        u_d = u_h.to(env.device, non_blocking=True)               # H2D  u
+        env.step(u_d)
+        v_h.copy_(env.values, non_blocking=True); b_h.copy_(env.adj_bits, non_blocking=True)
+        d_h.copy_(env.degree, non_blocking=True); r_h.copy_(env.reward, non_blocking=True)
+        if o_h is not None:
+            o_h.copy_(env.obs, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        one()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        one()
+    te = D.max(time.perf_counter() - t0)
+    nbytes = lambda t: t.numel() * t.element_size()
+    d2h = nbytes(u_h) + nbytes(v_h) + nbytes(b_h) + nbytes(d_h) + nbytes(r_h) + (nbytes(o_h) if o_h is not None else 0)
+    del env
+    torch.cuda.empty_cache()
+    return {"value": world * E * N * N * Ke / te, "unit": UNIT, "h2d_bytes_per_step": nbytes(u_h), "d2h_bytes_per_step": d2h,
+            "steps": Ke, "ms_per_step": te / Ke * 1e3,
+            "api": "FlockVecEnv(adjacency_mode='bitmask').controller()+step(u): adjacency bits + degree instead of the dense network"}
+
+
 def run_ours(args, cfg, rank, world, local_rank):
     if cfg.get("dropin"):
         out = run_dropin(args, cfg, rank)
@@ -530,6 +572,12 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     head = measure_env_config(D, args.config, cfg, rank, world, K, W, args.warmup_ms, args, with_diag=not args.no_extras)
     e2e = measure_e2e(D, cfg, rank, world, min(K, args.e2e_steps))
+    e2e_bits = None
+    if not args.no_extras:
+        try:
+            e2e_bits = measure_e2e_bitmask(D, cfg, rank, world, min(K, args.e2e_steps))
+        except Exception as e:
+            e2e_bits = {"error": repr(e)[:300]}
 
     # ---- every other BASELINE config, so that the driver's BENCH / SCALE records carry them --------------------------------
     extras = {}
@@ -571,7 +619,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                         "frac": 32 * E * N * N / step_s / 1e12 / fp_peak}},
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": head["clocks"],
                "extra": {"per_step_api": head.get("per_step_api"), "per_launch_us": head.get("per_launch_us"),
-                         "configs": extras}}
+                         "e2e_bitmask": e2e_bits, "configs": extras}}
         print(json.dumps(out), flush=True)
     D.close()
 

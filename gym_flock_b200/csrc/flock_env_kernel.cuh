@@ -135,7 +135,8 @@ template <typename T> struct TopK {
 // fused fp64); the row's own index (the diagonal, or an unused slot) sorts last.  The approximate order is almost always
 // right, so check first and run the insertion network only when some lane of the warp is out of order.
 // Returns the exact r2 of the KNN_K-th neighbour (+inf when the row has fewer).
-__device__ __forceinline__ double knn_rerank(const double4 xi, const int i, const double4 *xe, int (&id)[TOPK]) {
+template <typename XE>
+__device__ __forceinline__ double knn_rerank(const double4 xi, const int i, const XE &xe, int (&id)[TOPK]) {
     double key[TOPK];
 #pragma unroll
     for (int m = 0; m < TOPK; ++m) {
@@ -143,6 +144,13 @@ __device__ __forceinline__ double knn_rerank(const double4 xi, const int i, cons
         const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
         key[m] = (id[m] == i) ? CUDART_INF : __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     }
+    // the row itself (r2 = 0) leads the approximate ranking when the caller let the diagonal ride along: rotate it to the end
+    // (it sorts last) instead of paying for the network on every row
+    const bool lead = (id[0] == i);
+#pragma unroll
+    for (int m = 0; m + 1 < TOPK; ++m) { id[m] = lead ? id[m + 1] : id[m]; key[m] = lead ? key[m + 1] : key[m]; }
+    id[TOPK - 1] = lead ? i : id[TOPK - 1];
+    key[TOPK - 1] = lead ? CUDART_INF : key[TOPK - 1];
     bool sorted = true;
 #pragma unroll
     for (int m = 0; m + 1 < TOPK; ++m)
@@ -233,7 +241,7 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
 // two masks applied as exact factors 1.0 / 0.0 (x * 1.0 and + 0.0 are exact, so the sums are bit-identical to the
 // branchy form).  The caller passes a valid agent address even when the lane idles (low == 0): pv masks everything.
 //   !adjacent  : the candidate's bit is cleared in its mask word (shared-memory RED at waddr)
-#define FLOCK_REFINE_PRED_ASM(SECOND_NEWTON_STEP)                                                                  \
+#define FLOCK_REFINE_PRED_ASM(SECOND_NEWTON_STEP, LD_VEL, ...)                                                                  \
     asm volatile(                                                                                                   \
         "{\n\t"                                                                                                     \
         ".reg .pred pv, pa, pg, pr;\n\t"                                                                            \
@@ -241,7 +249,7 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
         ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c, ma, mg;\n\t"                      \
         "setp.ne.u32 pv, %10, 0;\n\t"                                                                               \
         "ld.shared.v2.f64 {xjx, xjy}, [%11];\n\t"                                                                   \
-        "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t"                                                                \
+        LD_VEL                                                                                                      \
         "sub.f64 dx, %13, xjx;\n\t"                                                                                 \
         "sub.f64 dy, %14, xjy;\n\t"                                                                                 \
         "mul.f64 r2, dy, dy;\n\t"                                                                                   \
@@ -281,15 +289,30 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
         : "+d"(A.f0), "+d"(A.f1), "+d"(A.f2), "+d"(A.f3), "+d"(A.f4), "+d"(A.f5), "+d"(A.gx), "+d"(A.gy), "+r"(deg),  \
           "+r"(left)                                                                                                \
         : "r"(low), "r"(xaddr), "r"(waddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm)            \
+          __VA_ARGS__                                                                                               \
         : "memory")
 
 template <bool NEWTON1>
 __device__ __forceinline__ void refine_fast_pred(const double4 xi, const unsigned xaddr, const unsigned low, const unsigned waddr,
                                                  const double R2, const double Rm, Acc &A, int &deg, int &left) {
     if constexpr (NEWTON1) {            // fp32 output mode: seed (2^-23) + one Newton step
-        FLOCK_REFINE_PRED_ASM("");
+        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t");
     } else {                            // fp64 output mode: two Newton steps (full double accuracy)
-        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t");
+        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t",
+                              "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t");
+    }
+}
+
+// the same with positions and velocities in two separate shared-memory arrays (flock_group_kernel): xaddr -> (px, py),
+// vaddr -> (vx, vy)
+template <bool NEWTON1>
+__device__ __forceinline__ void refine_fast_pred2(const double4 xi, const unsigned xaddr, const unsigned vaddr, const unsigned low,
+                                                  const unsigned waddr, const double R2, const double Rm, Acc &A, int &deg, int &left) {
+    if constexpr (NEWTON1) {
+        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%19];\n\t", , "r"(vaddr));
+    } else {
+        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t",
+                              "ld.shared.v2.f64 {xjz, xjw}, [%19];\n\t", , "r"(vaddr));
     }
 }
 

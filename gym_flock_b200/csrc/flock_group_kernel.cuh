@@ -54,6 +54,18 @@ struct GArgs {
 // to 256 threads, else 512
 constexpr int GMAXT = 512;
 
+// The CTA's agents in shared memory: positions and velocities in two arrays of 16-byte elements.  The refine loop loads
+// RANDOM agents (each lane its own candidate): 16-byte elements spread over 8 bank groups, a 32-byte struct over 4 -- the
+// step is bound by the L1 / shared-memory pipe, and those loads were half of its wavefronts.
+struct EnvState {
+    const double2 *p, *v;
+    __device__ __forceinline__ double4 operator[](const int j) const {
+        const double2 a = p[j], b = v[j];
+        return make_double4(a.x, a.y, b.x, b.y);
+    }
+    __device__ __forceinline__ EnvState operator+(const int k) const { return EnvState{p + k, v + k}; }
+};
+
 // ---- in-warp expansion of 32 consecutive rows of adj_mean, N a compile-time constant ---------------------------------
 // Row r of the warp lives N elements after row r-1: with N known every store address is dst + immediate, the mask word
 // and 1/deg loads use immediate offsets too, so a row costs two LDS, the bit -> value selects and one 16-byte store.
@@ -73,7 +85,26 @@ __device__ __forceinline__ void expand_rows_const(TO *wout, const unsigned *wm, 
         const TO *ip = idgs + (on ? sr : 0);
         TO *dst = wout + (on ? sr : 0) * NC + c;
         const int last = nrows - sr;                    // this lane stores while r < last
-        if (nrows == 32) {
+        if (nrows == 32 && rpi == 1) {
+            // four rows per shared-memory access: the mask words of consecutive rows (same word index) and their 1/deg are
+            // contiguous, so one LDS.128 each feeds four stores (the step is bound by the L1 / shared-memory pipe)
+#pragma unroll
+            for (int r4 = 0; r4 < 32; r4 += 4) {
+                const uint4 mw = *reinterpret_cast<const uint4 *>(mp + r4);
+                TO v0, v1, v2, v3;
+                if constexpr (sizeof(TO) == 4) {
+                    const float4 ig = *reinterpret_cast<const float4 *>(ip + r4);
+                    v0 = ig.x; v1 = ig.y; v2 = ig.z; v3 = ig.w;
+                } else {
+                    const double2 ia = *reinterpret_cast<const double2 *>(ip + r4), ib = *reinterpret_cast<const double2 *>(ip + r4 + 2);
+                    v0 = ia.x; v1 = ia.y; v2 = ib.x; v3 = ib.y;
+                }
+                store_group<TO, V>(dst + (r4 + 0) * NC, mw.x >> sh, v0, on);
+                store_group<TO, V>(dst + (r4 + 1) * NC, mw.y >> sh, v1, on);
+                store_group<TO, V>(dst + (r4 + 2) * NC, mw.z >> sh, v2, on);
+                store_group<TO, V>(dst + (r4 + 3) * NC, mw.w >> sh, v3, on);
+            }
+        } else if (nrows == 32) {
 #pragma unroll
             for (int r = 0; r < 32; r += rpi) {
                 const bool go = on && (rpi == 1 || r < last);
@@ -187,7 +218,8 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
             x = plain ? integrate_exact(x, u, a.dt, a.var.step_scale) : integrate_variant(x, u, i, a.dt, a.var);
         }
-        reinterpret_cast<double4 *>(smem + a.off_xs)[r] = x;
+        reinterpret_cast<double2 *>(smem + a.off_xs)[r] = make_double2(x.x, x.y);
+        reinterpret_cast<double2 *>(smem + a.off_xs + a.xs_bytes / 2)[r] = make_double2(x.z, x.w);
         if constexpr (PA32) {
             float *p = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem + a.off_pf) + g * NP2 + (i >> 1));
             p[i & 1] = (float)(x.x - ref.x); p[2 + (i & 1)] = (float)(x.y - ref.y);
@@ -199,7 +231,8 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
     for (int t = 0; t < steps; ++t) {
         const unsigned par = (unsigned)(t & 1);
         const bool last_step = (t == steps - 1);
-        const double4 *xs = reinterpret_cast<const double4 *>(smem + a.off_xs + par * a.xs_bytes);
+        const EnvState xs{reinterpret_cast<const double2 *>(smem + a.off_xs + par * a.xs_bytes),
+                          reinterpret_cast<const double2 *>(smem + a.off_xs + par * a.xs_bytes + a.xs_bytes / 2)};
         const float4 *pf = reinterpret_cast<const float4 *>(smem + a.off_pf + par * a.pf_bytes);
         double *stats = reinterpret_cast<double *>(smem + a.off_stats + par * a.stats_bytes);
         __syncthreads();                                   // the state of step t is complete; everybody left step t-1
@@ -208,7 +241,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         {
             const int warp = tid >> 5, nwarps = blockDim.x >> 5;
             for (int ge = warp; ge < genv; ge += nwarps) {
-                const double4 *xe = xs + ge * N;
+                const EnvState xe = xs + ge * N;
                 const double rx = xe[0].z, ry = xe[0].w;    // sums about agent 0's velocity (a member of the flock)
                 double sx = 0, sy = 0, qx = 0, qy = 0;
                 for (int j = lane; j < N; j += 32) {
@@ -231,7 +264,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         }
 
         if (tid - lane >= nrows) continue;                // a warp without rows (a CTA of the tail round) only keeps the barrier
-        const double4 *xe = xs + g * N;
+        const EnvState xe = xs + g * N;
         const double4 xi = xe[i];
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
 
@@ -374,7 +407,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     top.insert(fma(dx, dx, dy * dy), j);
                 }
             };
-            // The mask holds every agent with r2 <= tau (the filter has no false negatives).  If the 7th neighbour found in it is
+            // The mask holds every agent with r2 <= tau (the filter has no false negatives; the row itself is skipped).  If the 7th neighbour found in it is
             // itself within tau, no agent outside the mask can be closer: done.  Otherwise (no usable hint: first step,
             // teleported agents, N <= 8) the warp searches all N agents.
             int nb[TOPK];
@@ -388,12 +421,21 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     top.init(i);
                 }
                 if (use_mask) {
-                    for (int w = 0; w < nw; ++w) {
-                        unsigned b = mkrow[w * GMS];
-                        while (b) { const int j = w * 32 + __ffs(b) - 1; b &= b - 1; if (j < N) consider(j); }
+                    // one flat loop over the lane's mask bits (the advance to the next word is part of the body, as in the
+                    // refine loop): a warp iterates max-over-lanes(candidates) times, not the sum of the per-word maxima
+                    unsigned b = mkrow[0];
+                    int w = 0, left = valid ? cntk : 0;
+                    while (left > 0) {
+                        if (b == 0) { ++w; b = mkrow[w * GMS]; }
+                        if (b != 0) {
+                            const int j = w * 32 + __ffs(b) - 1;
+                            b &= b - 1;
+                            --left;
+                            if (j != i) consider(j);
+                        }
                     }
                 } else {
-                    for (int j = 0; j < N; ++j) consider(j);
+                    for (int j = 0; j < N; ++j) if (j != i) consider(j);
                 }
                 __syncwarp();
 #pragma unroll
@@ -458,9 +500,10 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
             mrow[(i >> 5) * GMS] &= ~(1u << (i & 31));
             --cnt;
-            const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe);
+            const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe.p);
+            const unsigned voff = a.xs_bytes / 2;             // the velocity array follows the position array
             unsigned waddr = (unsigned)__cvta_generic_to_shared(mrow);
-            const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 32u : 0u);
+            const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 16u : 0u);
             unsigned cand = mrow[0], nxt = mrow[GMS];         // (the mask region has one spare word row)
             int jb = 0;
             int left = valid ? cnt : 0;
@@ -475,8 +518,8 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 const unsigned low = cand & (0u - cand);
                 cand ^= low;
                 const int j = jb + bfind(low);
-                const unsigned xaddr = low ? xe_s + (unsigned)j * 32u : xdummy;
-                refine_fast_pred<PA32>(xi, xaddr, low, waddr, R2r, Rmr, A, deg, left);
+                const unsigned xaddr = low ? xe_s + (unsigned)j * 16u : xdummy;
+                refine_fast_pred2<PA32>(xi, xaddr, xaddr + voff, low, waddr, R2r, Rmr, A, deg, left);
             }
         }
         __syncwarp();
@@ -522,7 +565,8 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 const double2 u = make_double2(ux, uy);
                 const bool plain = (a.var.u_clip == 0.0) && (a.var.n_leaders == 0) && (a.var.state_scale == 1.0);
                 const double4 xn = plain ? integrate_exact(xi, u, a.dt, a.var.step_scale) : integrate_variant(xi, u, i, a.dt, a.var);
-                reinterpret_cast<double4 *>(smem + a.off_xs + (par ^ 1u) * a.xs_bytes)[r] = xn;
+                reinterpret_cast<double2 *>(smem + a.off_xs + (par ^ 1u) * a.xs_bytes)[r] = make_double2(xn.x, xn.y);
+                reinterpret_cast<double2 *>(smem + a.off_xs + (par ^ 1u) * a.xs_bytes + a.xs_bytes / 2)[r] = make_double2(xn.z, xn.w);
                 if constexpr (PA32) {
                     const double ox = xe[0].x, oy = xe[0].y;   // env origin: agent 0 before the step
                     float *p = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem + a.off_pf + (par ^ 1u) * a.pf_bytes) + g * NP2 + (i >> 1));
