@@ -227,12 +227,6 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         }
     }
 
-    const bool env_sync = (a.G <= 15);
-    // the envs this warp holds rows of (none: g_lo > g_hi)
-    const int g_lo = min(tid - lane, max(nrows - 1, 0)) / N;
-    const int g_hi = (tid - lane < nrows) ? min(tid - lane + 31, nrows - 1) / N : g_lo - 1;
-    __syncthreads();                                       // step 0: the staged state is complete
-
 #pragma unroll 1
     for (int t = 0; t < steps; ++t) {
         const unsigned par = (unsigned)(t & 1);
@@ -241,27 +235,12 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                           reinterpret_cast<const double2 *>(smem + a.off_xs + par * a.xs_bytes + a.xs_bytes / 2)};
         const float4 *pf = reinterpret_cast<const float4 *>(smem + a.off_pf + par * a.pf_bytes);
         double *stats = reinterpret_cast<double *>(smem + a.off_stats + par * a.stats_bytes);
-        // ---- synchronisation between steps: PER ENV.  Step t+1 of a row only needs the new state of its own env, i.e. the
-        //      3-4 warps that hold the env's rows -- a named barrier per env (id 1 + g, the env's warps) instead of a block-wide
-        //      one, so a slow warp (the refine loop is data dependent) holds up its env, not the CTA.  (ncu: 19 % of the warp
-        //      samples sat at the block barrier.)  A warp that straddles two envs joins both, lower env first.  More than 15
-        //      envs per CTA (tiny N): the block barrier.
-        if (env_sync) {
-            if (t > 0) {
-                for (int ge = g_lo; ge <= g_hi; ++ge) {
-                    const int w0 = (ge * N) >> 5, w1 = ((ge + 1) * N - 1) >> 5;
-                    if (w1 > w0) asm volatile("bar.sync %0, %1;" ::"r"(1 + ge), "r"(32 * (w1 - w0 + 1)) : "memory");
-                    else __syncwarp();
-                }
-            }
-        } else {
-            if (t > 0) __syncthreads();                    // the state of step t is complete; everybody left step t-1
-        }
+        __syncthreads();                                   // the state of step t is complete; everybody left step t-1
 
-        // ---- per-env velocity sums and reward: one warp per env (the env's first warp), published through a step counter ----
+        // ---- per-env velocity sums and reward: one warp per env, published through a step counter -----------------------
         {
             const int warp = tid >> 5, nwarps = blockDim.x >> 5;
-            auto env_stats = [&](const int ge) {
+            for (int ge = warp; ge < genv; ge += nwarps) {
                 const EnvState xe = xs + ge * N;
                 const double rx = xe[0].z, ry = xe[0].w;    // sums about agent 0's velocity (a member of the flock)
                 double sx = 0, sy = 0, qx = 0, qy = 0;
@@ -281,18 +260,10 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     __threadfence_block();
                     reinterpret_cast<volatile double *>(st)[2] = (double)(t + 1);            // ready
                 }
-            };
-            if (env_sync) {
-                for (int ge = g_lo; ge <= g_hi; ++ge) if (((ge * N) >> 5) == warp) env_stats(ge);
-            } else {
-                for (int ge = warp; ge < genv; ge += nwarps) env_stats(ge);
             }
         }
 
-        if (tid - lane >= nrows) {                        // a warp without rows (a CTA of the tail round)
-            if (env_sync) break;
-            continue;                                     // (block-barrier mode: it keeps arriving)
-        }
+        if (tid - lane >= nrows) continue;                // a warp without rows (a CTA of the tail round) only keeps the barrier
         const EnvState xe = xs + g * N;
         const double4 xi = xe[i];
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
