@@ -96,6 +96,12 @@ class FlockVecEnv:
     def _ptr(t):
         return None if t is None else ctypes.c_void_p(t.data_ptr())
 
+    def _device_ctx(self):
+        """torch.cuda.device(...) only when this thread's current device is not the env's (the context manager costs more
+        than a launch)."""
+        import contextlib
+        return contextlib.nullcontext() if torch.cuda.current_device() == self.device.index else torch.cuda.device(self.device)
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -115,7 +121,7 @@ class FlockVecEnv:
     def _launch(self, x_in, u_in, x_out, u_next, want_obs=True, aux=None):
         if aux is None:
             aux = self._aux if want_obs else _lib.FlockAux(self.nonfinite.data_ptr(), None, None, None, None, None)
-        with torch.cuda.device(self.device):
+        with self._device_ctx():
             _lib.check(self._fn_step(self._pp, self._ptr(x_in), self._ptr(u_in), self._ptr(x_out),
                                      self._ptr(self.values) if want_obs else None,
                                      self._ptr(self.network) if want_obs else None,
