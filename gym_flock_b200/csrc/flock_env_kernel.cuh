@@ -241,22 +241,23 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
 // two masks applied as exact factors 1.0 / 0.0 (x * 1.0 and + 0.0 are exact, so the sums are bit-identical to the
 // branchy form).  The caller passes a valid agent address even when the lane idles (low == 0): pv masks everything.
 //   !adjacent  : the candidate's bit is cleared in its mask word (shared-memory RED at waddr)
-#define FLOCK_REFINE_PRED_ASM(SECOND_NEWTON_STEP, LD_VEL, ...)                                                                  \
+#define FLOCK_REFINE_PRED_ASM(SECOND_NEWTON_STEP, LD_VEL, EXTRA_BODY, EXTRA_IN)                                   \
     asm volatile(                                                                                                   \
         "{\n\t"                                                                                                     \
         ".reg .pred pv, pa, pg, pr;\n\t"                                                                            \
         ".reg .b32 nl, hi;\n\t"                                                                                     \
         ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c, ma, mg;\n\t"                      \
-        "setp.ne.u32 pv, %10, 0;\n\t"                                                                               \
-        "ld.shared.v2.f64 {xjx, xjy}, [%11];\n\t"                                                                   \
+        "setp.ne.u32 pv, %11, 0;\n\t"                                                                            \
+        "ld.shared.v2.f64 {xjx, xjy}, [%12];\n\t"                                                              \
         LD_VEL                                                                                                      \
-        "sub.f64 dx, %13, xjx;\n\t"                                                                                 \
-        "sub.f64 dy, %14, xjy;\n\t"                                                                                 \
+        "sub.f64 dx, %14, xjx;\n\t"                                                                              \
+        "sub.f64 dy, %15, xjy;\n\t"                                                                              \
         "mul.f64 r2, dy, dy;\n\t"                                                                                   \
         "fma.rn.f64 r2, dx, dx, r2;\n\t"                                                                            \
-        "setp.lt.and.f64 pa, r2, %17, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                          \
-        "setp.le.and.f64 pg, r2, %18, pv;\n\t"  /* gradient mask: r2 <= Rm */                                       \
-        "setp.geu.and.f64 pr, r2, %17, pv;\n\t" /* a candidate that is not a neighbour */                           \
+        EXTRA_BODY                                                                                                  \
+        "setp.lt.and.f64 pa, r2, %18, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                        \
+        "setp.le.and.f64 pg, r2, %19, pv;\n\t"  /* gradient mask: r2 <= Rm */                                     \
+        "setp.geu.and.f64 pr, r2, %18, pv;\n\t" /* a candidate that is not a neighbour */                         \
         "selp.b32 hi, 0x3FF00000, 0, pa;\n\t"                                                                       \
         "mov.b64 ma, {0, hi};\n\t"              /* 1.0 or 0.0 */                                                    \
         "selp.b32 hi, 0x3FF00000, 0, pg;\n\t"                                                                       \
@@ -269,51 +270,70 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
         "mul.f64 ya, y, ma;\n\t"                                                                                    \
         "mul.f64 yg, y, mg;\n\t"                                                                                    \
         "mul.f64 y4, ya, ya;\n\t"                                                                                   \
-        "sub.f64 dvx, %15, xjz;\n\t"                                                                                \
-        "sub.f64 dvy, %16, xjw;\n\t"                                                                                \
-        "fma.rn.f64 %0, dvx, ma, %0;\n\t"                                                                           \
-        "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                            \
-        "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                            \
-        "fma.rn.f64 %3, dvy, ma, %3;\n\t"                                                                           \
-        "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                            \
-        "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                            \
+        "sub.f64 dvx, %16, xjz;\n\t"                                                                             \
+        "sub.f64 dvy, %17, xjw;\n\t"                                                                             \
+        "fma.rn.f64 %0, dvx, ma, %0;\n\t"                                                                     \
+        "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                      \
+        "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                      \
+        "fma.rn.f64 %3, dvy, ma, %3;\n\t"                                                                     \
+        "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                      \
+        "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                      \
         "neg.f64 c, yg;\n\t"                                                                                        \
         "fma.rn.f64 c, c, yg, yg;\n\t" /* 1/r2 - 1/r4 */                                                            \
-        "fma.rn.f64 %6, dx, c, %6;\n\t"                                                                             \
-        "fma.rn.f64 %7, dy, c, %7;\n\t"                                                                             \
-        "@pa add.s32 %8, %8, 1;\n\t"                                                                                \
-        "@pv add.s32 %9, %9, -1;\n\t"                                                                               \
-        "not.b32 nl, %10;\n\t"                                                                                      \
-        "@pr red.shared.and.b32 [%12], nl;\n\t"                                                                     \
+        "fma.rn.f64 %6, dx, c, %6;\n\t"                                                                       \
+        "fma.rn.f64 %7, dy, c, %7;\n\t"                                                                       \
+        "@pa add.s32 %8, %8, 1;\n\t"                                                                        \
+        "@pv add.s32 %9, %9, -1;\n\t"                                                                     \
+        "not.b32 nl, %11;\n\t"                                                                                   \
+        "@pr red.shared.and.b32 [%13], nl;\n\t"                                                                \
         "}"                                                                                                         \
         : "+d"(A.f0), "+d"(A.f1), "+d"(A.f2), "+d"(A.f3), "+d"(A.f4), "+d"(A.f5), "+d"(A.gx), "+d"(A.gy), "+r"(deg),  \
-          "+r"(left)                                                                                                \
-        : "r"(low), "r"(xaddr), "r"(waddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm)            \
-          __VA_ARGS__                                                                                               \
+          "+r"(left), "=f"(r2f) /* %10: the pair's r2 as an fp32 key, written by EXTRA_BODY only */                  \
+        : "r"(low), "r"(xaddr), "r"(waddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm) EXTRA_IN   \
         : "memory")
+
+#define FLOCK_NEWTON2 "fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t"
+#define FLOCK_NOTHING
 
 template <bool NEWTON1>
 __device__ __forceinline__ void refine_fast_pred(const double4 xi, const unsigned xaddr, const unsigned low, const unsigned waddr,
                                                  const double R2, const double Rm, Acc &A, int &deg, int &left) {
+    [[maybe_unused]] float r2f;
     if constexpr (NEWTON1) {            // fp32 output mode: seed (2^-23) + one Newton step
-        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t");
+        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%12+16];\n\t", "", FLOCK_NOTHING);
     } else {                            // fp64 output mode: two Newton steps (full double accuracy)
-        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t",
-                              "ld.shared.v2.f64 {xjz, xjw}, [%11+16];\n\t");
+        FLOCK_REFINE_PRED_ASM(FLOCK_NEWTON2, "ld.shared.v2.f64 {xjz, xjw}, [%12+16];\n\t", "", FLOCK_NOTHING);
     }
 }
 
 // the same with positions and velocities in two separate shared-memory arrays (flock_group_kernel): xaddr -> (px, py),
 // vaddr -> (vx, vy)
+#define FLOCK_VADDR_IN , "r"(vaddr)
 template <bool NEWTON1>
 __device__ __forceinline__ void refine_fast_pred2(const double4 xi, const unsigned xaddr, const unsigned vaddr, const unsigned low,
                                                   const unsigned waddr, const double R2, const double Rm, Acc &A, int &deg, int &left) {
+    [[maybe_unused]] float r2f;
     if constexpr (NEWTON1) {
-        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%19];\n\t", , "r"(vaddr));
+        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%20];\n\t", "", FLOCK_VADDR_IN);
     } else {
-        FLOCK_REFINE_PRED_ASM("fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\tfma.rn.f64 y, y, c, y;\n\t",
-                              "ld.shared.v2.f64 {xjz, xjw}, [%19];\n\t", , "r"(vaddr));
+        FLOCK_REFINE_PRED_ASM(FLOCK_NEWTON2, "ld.shared.v2.f64 {xjz, xjw}, [%20];\n\t", "", FLOCK_VADDR_IN);
     }
+}
+
+// ... and returning the pair's r2 as an fp32 selection key for Flocking-v0's kNN (0xFFFFFFFF when the lane idles): the refine
+// loop already has the exact r2 of every candidate, so the kNN search rides along instead of running its own pass
+#define FLOCK_R2KEY_BODY "cvt.rn.f32.f64 %10, r2;\n\t"
+template <bool NEWTON1>
+__device__ __forceinline__ float refine_fast_pred2_key(const double4 xi, const unsigned xaddr, const unsigned vaddr, const unsigned low,
+                                                       const unsigned waddr, const double R2, const double Rm, Acc &A, int &deg,
+                                                       int &left) {
+    float r2f;
+    if constexpr (NEWTON1) {
+        FLOCK_REFINE_PRED_ASM("", "ld.shared.v2.f64 {xjz, xjw}, [%20];\n\t", FLOCK_R2KEY_BODY, FLOCK_VADDR_IN);
+    } else {
+        FLOCK_REFINE_PRED_ASM(FLOCK_NEWTON2, "ld.shared.v2.f64 {xjz, xjw}, [%20];\n\t", FLOCK_R2KEY_BODY, FLOCK_VADDR_IN);
+    }
+    return r2f;
 }
 
 // ---- in-warp expansion of the warp's rows of adj_mean (small rows) -----------------------------------------------

@@ -5,6 +5,9 @@
 tag=${1:-rX}; G=${2:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511"
 err=gpurun_out/${tag}_${G}gpu.err
+# insurance: the parity suite must be green on this build before 8 GPUs are spent on it
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/${tag}_pytest_${G}gpu.log 2>&1 || { tail -20 gpurun_out/${tag}_pytest_${G}gpu.log; exit 1; }
+tail -2 gpurun_out/${tag}_pytest_${G}gpu.log
 $TR tools/swarm_check.py 2048 8192 65536 > gpurun_out/${tag}_swarm_check_${G}gpu.txt 2> $err
 cat gpurun_out/${tag}_swarm_check_${G}gpu.txt
 $TR bench.py --gpus $G --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench_${G}gpu.json 2>> $err
