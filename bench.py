@@ -309,7 +309,7 @@ def measure_env_config(D, name, cfg, rank, world, K, W, warm_ms, args, with_diag
     from gym_flock_b200.synthetic import initial_states_fast
     E, N, prec = envs_per_gpu(cfg, world), cfg["N"], cfg["precision"]
     knn = cfg["env_id"] == "Flocking-v0"
-    x0 = initial_states_fast(E, N, seed=1234 + rank * E)
+    x0 = initial_states_fast(E, N, seed=1234 + (rank + args.seed_rank) * E)
     env = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=D.device,
                       adjacency_mode=args.adjacency, lanes=args.env_lanes, tune=args.tune)
     env.reset(x0)
@@ -640,6 +640,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=32, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
     ap.add_argument("--env-lanes", type=int, default=0, help="env batches: threads per row (0 = library heuristic)")
     ap.add_argument("--tune", type=lambda v: int(v, 0), default=0, help="FlockParams.reserved diagnostics word (A/B runs)")
+    ap.add_argument("--seed-rank", type=int, default=0, help="diagnostics: use the synthetic states rank R of a multi-GPU run would get")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()
