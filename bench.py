@@ -370,9 +370,11 @@ def measure_swarm(D, cfg, rank, world, K, W, args, adjacency, skip_gather=False,
     x0 = initial_states_fast(1, N, seed=1234, law="density")[0]
     env = SwarmEnv(cfg["env_id"], n_agents=N, precision=prec, device=D.device, adjacency_mode=adjacency, lanes=lanes)
     env.reset(x0)
+    env._skip_gather = bool(skip_gather)
+    if args.swarm_graph:
+        env.capture_graphs()
     for _ in range(W):
         env.step()
-    env._skip_gather = bool(skip_gather)
     sampler = ClockSampler(D.device.index)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -395,6 +397,7 @@ def measure_swarm(D, cfg, rank, world, K, W, args, adjacency, skip_gather=False,
            "adjacency": adjacency, "skip_gather": bool(skip_gather), "algorithmic_bytes_per_step": alg,
            "achieved_gbs": alg / step_s / 1e9, "frac": alg / step_s / 1e9 / peaks["hbm_gbs"], "clocks": clocks,
            "launches": K * 3 + (K if world > 1 and not skip_gather else 0), "peak_source": peak_src,
+           "cuda_graph": bool(args.swarm_graph),
            "kernel": "flock_prep_kernel + flock_swarm_kernel + flock_knn_fix_kernel (per GPU)"}
     del env
     torch.cuda.empty_cache()
@@ -640,6 +643,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=32, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
     ap.add_argument("--env-lanes", type=int, default=0, help="env batches: threads per row (0 = library heuristic)")
     ap.add_argument("--tune", type=lambda v: int(v, 0), default=0, help="FlockParams.reserved diagnostics word (A/B runs)")
+    ap.add_argument("--swarm-graph", type=int, default=1, help="C5: replay one CUDA graph per step (prep + row + fix-up + all-gather)")
     ap.add_argument("--seed-rank", type=int, default=0, help="diagnostics: use the synthetic states rank R of a multi-GPU run would get")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")

@@ -44,7 +44,7 @@ struct GArgs {
     double thrC, R2, Rm, dt, inv_ascale, ulim;
     StepVariant var;
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
-    unsigned off_hint;        // Flocking-v0: last step's neighbours [T][8] u16
+    unsigned off_masks2, off_hint;   // Flocking-v0: kNN candidate mask (same layout as masks), last step's neighbours [T][8] u16
     unsigned xs_bytes, pf_bytes, stats_bytes;    // size of ONE copy of the parity-duplicated arrays
     int obs_direct;           // Flocking-v0: every lane stores its own observation row (7 x 16 bytes) instead of staging the
                               // warp's rows in shared memory for a fully coalesced copy (no staging area: more CTAs per SM)
@@ -269,16 +269,16 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
 
         // ---- phase A: filter over all N pairs; candidate bits in shared memory, bit k of the row <-> agent k ------------------
-        // Flocking-v0 (KNN): the candidate radius of the row is widened to tau, an UPPER BOUND on its 7th-nearest distance derived
-        // from last step's neighbours (the 7 nearest of this step are among the agents at least as close as the farthest of ANY
-        // 7 agents; neighbourhoods change slowly, so tau is rarely far beyond the communication radius).  The refine loop then
-        // sees every agent within tau and the kNN search rides along on the exact r2 it computes anyway.  The hint only sets a
-        // radius: stale, missing or garbage hints cost time (the warp falls back to all N), never correctness.
-        int cnt = 0;
+        // Flocking-v0 (KNN): a second mask collects the agents within tau, an UPPER BOUND on the row's 7th-nearest distance
+        // derived from last step's neighbours (the 7 nearest of this step are among the agents at least as close as the
+        // farthest of ANY 7 agents); neighbourhoods change slowly, so that mask holds 7-10 agents instead of N.  The hint
+        // only sets the radius: stale, missing or garbage hints cost time (a mask with < 7 agents falls back to all N),
+        // never correctness.
+        int cnt = 0, cntk = 0;
         int nw;
+        [[maybe_unused]] unsigned *mkrow = reinterpret_cast<unsigned *>(smem + a.off_masks2) + tid;
         [[maybe_unused]] unsigned short *hint = reinterpret_cast<unsigned short *>(smem + a.off_hint) + tid * 8;
         [[maybe_unused]] double tau = 0.0;
-        [[maybe_unused]] bool usable = false;
         if constexpr (KNN) {
 #pragma unroll
             for (int m = 0; m < KNN_K; ++m) {
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 tau = fmax(tau, fma(dx, dx, dy * dy));
             }
             tau *= 1.0 + 1e-12;                              // (covers fused vs unfused rounding of the same distance)
-            usable = (tau > 0.0) && (tau <= 4.0 * a.thrC);   // a radius far beyond the communication range is no help
         }
         if constexpr (PA32) {
             const int nslots = NP2;
@@ -296,20 +295,21 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             const float *pif = reinterpret_cast<const float *>(pe + (i >> 1));
             const float pxi = pif[i & 1], pyi = pif[2 + (i & 1)];
             const float2 nx = make_float2(-pxi, -pxi), ny = make_float2(-pyi, -pyi);
-            // conservative per-row threshold (covers the fp32 rounding of both positions and of the fused form)
+            // conservative per-row thresholds (cover the fp32 rounding of both positions and of the fused form)
             const float pm = fmaxf(fabsf(pxi), fabsf(pyi));
-            float thrA = fmaf(a.thr_b, pm + a.thr_c, a.thr_a);
-            if constexpr (KNN) {
-                if (usable) {
-                    const float tk = __double2float_ru(tau), rk = sqrtf(tk);
-                    thrA = fmaxf(thrA, tk * (1.0f + 3e-6f) + 16.0f * rk * (pm + 2.0f * rk) * 5.9604645e-8f);
-                }
-            }
+            const float thrA = fmaf(a.thr_b, pm + a.thr_c, a.thr_a);
             const float2 nthr2 = make_float2(-thrA, -thrA);
+            [[maybe_unused]] float2 nthrk2 = nthr2;
+            if constexpr (KNN) {
+                const float tk = __double2float_ru(tau), rk = sqrtf(tk);
+                const float thrK = tk * (1.0f + 3e-6f) + 16.0f * rk * (pm + 2.0f * rk) * 5.9604645e-8f;
+                nthrk2 = make_float2(-thrK, -thrK);
+            }
             // s = dx^2 + (dy^2 - thr): the candidate test is the SIGN of s; one funnel shift per pair moves it into the word
             // (first pair ends up highest: one BREV per word)
             auto word = [&](const int w, const int tend, auto FULL) {
                 unsigned bits = 0;
+                [[maybe_unused]] unsigned bitsk = 0;
                 const int tbase = w * 16;
                 auto body = [&](const int tt) {
                     const float4 q = pe[tbase + tt];
@@ -318,18 +318,26 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     const float2 s = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthr2));
                     bits = __funnelshift_l(__float_as_uint(s.x), bits, 1);
                     bits = __funnelshift_l(__float_as_uint(s.y), bits, 1);
+                    if constexpr (KNN) {
+                        const float2 sk = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, nthrk2));
+                        bitsk = __funnelshift_l(__float_as_uint(sk.x), bitsk, 1);
+                        bitsk = __funnelshift_l(__float_as_uint(sk.y), bitsk, 1);
+                    }
                 };
                 constexpr int CT = decltype(FULL)::value;        // > 0: compile-time slot count of this word
                 if constexpr (CT > 0) {
 #pragma unroll
                     for (int tt = 0; tt < CT; ++tt) body(tt);
                     bits = __brev(bits) >> (32 - 2 * CT);
+                    if constexpr (KNN) bitsk = __brev(bitsk) >> (32 - 2 * CT);
                 } else {
                     for (int tt = 0; tt < tend; ++tt) body(tt);
                     bits = __brev(bits) >> (32 - 2 * tend);          // 0 < tend <= 16
+                    if constexpr (KNN) bitsk = __brev(bitsk) >> (32 - 2 * tend);
                 }
                 mrow[w * GMS] = bits;
                 cnt += __popc(bits);
+                if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
             };
             if constexpr (NC != 0) {
                 constexpr int NS = (NC + 1) / 2, FW = NS / 16, TAIL = NS - FW * 16;
@@ -345,10 +353,11 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             }
         } else {
             nw = (N + 31) >> 5;
-            double thrC = a.thrC;
-            if constexpr (KNN) { if (usable) thrC = fmax(thrC, tau); }
+            const double thrC = a.thrC;
+            [[maybe_unused]] const double thrK = tau;
             for (int w = 0; w * 32 < N; ++w) {
                 unsigned bits = 0;
+                [[maybe_unused]] unsigned bitsk = 0;
                 const int kbase = w * 32;
                 const int kend = min(32, N - kbase);
                 auto body = [&](const int kk) {
@@ -357,6 +366,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     const double dx = xi.x - xj.x, dy = xi.y - xj.y;
                     const double r2 = fma(dx, dx, dy * dy);
                     bits |= (r2 <= thrC) ? (1u << kk) : 0u;
+                    if constexpr (KNN) bitsk |= (r2 <= thrK) ? (1u << kk) : 0u;
                 };
                 if (kend == 32) {
 #pragma unroll 8
@@ -366,23 +376,126 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 }
                 mrow[w * GMS] = bits;
                 cnt += __popc(bits);
+                if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
+            }
+        }
+
+        // ---- kNN observation: obs[i, 4m:4m+4] = x_i - x_nbr(m), staged per warp and stored coalesced      flocking.py:20-24
+        if constexpr (KNN) {
+            constexpr bool KPACK = PA32;
+            // Selection keys.  fp32 mode: the fp32 bits of r2 (non-negative, so they order as unsigned integers) with the low
+            // ceil(log2 N) mantissa bits replaced by the agent index -- a branch-free min/max network; fp64 mode: fused fp64 r2.
+            // Both keep TOPK = 9 survivors (the row itself + 7 + one slack slot); knn_rerank orders them exactly.
+            TopK<double> top;
+            unsigned kp[TOPK];
+            unsigned kidx = 1;
+            if constexpr (KPACK) {
+                while ((int)kidx < N) kidx <<= 1;
+                kidx -= 1;
+            }
+            auto consider = [&](const int j) {
+                if constexpr (KPACK) {
+                    const float *pj = reinterpret_cast<const float *>(pf + g * NP2 + (j >> 1));
+                    const float *pif = reinterpret_cast<const float *>(pf + g * NP2 + (i >> 1));
+                    const float dx = pj[j & 1] - pif[i & 1], dy = pj[2 + (j & 1)] - pif[2 + (i & 1)];
+                    unsigned k = (__float_as_uint(fmaf(dx, dx, dy * dy)) & ~kidx) | (unsigned)j;
+#pragma unroll
+                    for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
+                } else {
+                    const double4 xj = xe[j];
+                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                    top.insert(fma(dx, dx, dy * dy), j);
+                }
+            };
+            // The mask holds every agent with r2 <= tau (the filter has no false negatives; the row itself is skipped).  If the 7th neighbour found in it is
+            // itself within tau, no agent outside the mask can be closer: done.  Otherwise (no usable hint: first step,
+            // teleported agents, N <= 8) the warp searches all N agents.
+            int nb[TOPK];
+            bool use_mask = __all_sync(__activemask(), !valid || cntk >= KNN_K + 1) && N > KNN_K + 1;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if constexpr (KPACK) {
+#pragma unroll
+                    for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;
+                } else {
+                    top.init(i);
+                }
+                if (use_mask) {
+                    // one flat loop over the lane's mask bits (the advance to the next word is part of the body, as in the
+                    // refine loop): a warp iterates max-over-lanes(candidates) times, not the sum of the per-word maxima
+                    unsigned b = mkrow[0];
+                    int w = 0, left = valid ? cntk : 0;
+                    while (left > 0) {
+                        if (b == 0) { ++w; b = mkrow[w * GMS]; }
+                        if (b != 0) {
+                            const int j = w * 32 + __ffs(b) - 1;
+                            b &= b - 1;
+                            --left;
+                            if (j != i) consider(j);
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < N; ++j) if (j != i) consider(j);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < TOPK; ++m) {
+                    if constexpr (KPACK) nb[m] = (int)(kp[m] & kidx);
+                    else nb[m] = top.id[m];
+                }
+                const double key7 = knn_rerank(xi, i, xe, nb);
+                if (!use_mask || __all_sync(__activemask(), !valid || key7 <= tau)) break;
+                use_mask = false;
+            }
+#pragma unroll
+            for (int m = 0; m < KNN_K; ++m) hint[m] = (unsigned short)nb[m];           // next step's radius comes from these
+            if (a.aux.knn_hint != nullptr && last_step && valid) {
+                uint4 hv;
+                hv.x = (unsigned)nb[0] | ((unsigned)nb[1] << 16); hv.y = (unsigned)nb[2] | ((unsigned)nb[3] << 16);
+                hv.z = (unsigned)nb[4] | ((unsigned)nb[5] << 16); hv.w = (unsigned)nb[6];
+                reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
+            }
+            if (a.obs && a.obs_direct) {
+                if (valid) {
+                    TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
+#pragma unroll
+                    for (int m = 0; m < KNN_K; ++m) {
+                        const double4 xn = xe[nb[m]];
+                        if constexpr (PA32) {
+                            __stcs(reinterpret_cast<float4 *>(o) + m, make_float4((float)(xi.x - xn.x), (float)(xi.y - xn.y),
+                                                                                  (float)(xi.z - xn.z), (float)(xi.w - xn.w)));
+                        } else {
+                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m, make_double2(xi.x - xn.x, xi.y - xn.y));
+                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m + 1, make_double2(xi.z - xn.z, xi.w - xn.w));
+                        }
+                    }
+                }
+            } else if (a.obs) {
+                TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
+                TO *o = obs_w + lane * (NXS * KNN_K);
+#pragma unroll
+                for (int m = 0; m < KNN_K; ++m) {            // the diagonal and unused slots sort last: a zero block (N <= 7)
+                    const double4 xn = xe[nb[m]];
+                    o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
+                    o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+                }
+                __syncwarp();
+                const int wr0 = tid - lane;                  // first row of this warp within the CTA
+                const int nrw = min(32, nrows - wr0);
+                if (nrw > 0) {
+                    const int nvec = nrw * (NXS * KNN_K) * (int)sizeof(TO) / 16;
+                    const float4 *src = reinterpret_cast<const float4 *>(obs_w);
+                    float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<TO *>(a.obs) + ((size_t)e0 * N + wr0) * (NXS * KNN_K));
+                    for (int v = lane; v < nvec; v += 32) __stcs(dst + v, src[v]);
+                }
+                __syncwarp();
             }
         }
 
         // ---- phase B: refine the candidates in fp64, ascending j; the words end up holding the exact adjacency bits -------
-        // Flocking-v0: every candidate's r2 also enters a branch-free min/max network as a packed key -- the fp32 bits of r2
-        // (non-negative, so they order as unsigned integers) with the low ceil(log2 N) mantissa bits replaced by the agent index.
         Acc A;
         A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
         int deg = 0;
-        [[maybe_unused]] unsigned kp[TOPK];
-        [[maybe_unused]] unsigned kidx = 1;
-        if constexpr (KNN) {
-            while ((int)kidx < N) kidx <<= 1;
-            kidx -= 1;
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;     // unused slot: "self", at +inf
-        }
         {
             // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
             mrow[(i >> 5) * GMS] &= ~(1u << (i & 31));
@@ -406,87 +519,10 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 cand ^= low;
                 const int j = jb + bfind(low);
                 const unsigned xaddr = low ? xe_s + (unsigned)j * 16u : xdummy;
-                if constexpr (KNN) {
-                    const float r2f = refine_fast_pred2_key<PA32>(xi, xaddr, xaddr + voff, low, waddr, R2r, Rmr, A, deg, left);
-                    unsigned k = low ? ((__float_as_uint(r2f) & ~kidx) | (unsigned)j) : 0xFFFFFFFFu;
-#pragma unroll
-                    for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
-                } else {
-                    refine_fast_pred2<PA32>(xi, xaddr, xaddr + voff, low, waddr, R2r, Rmr, A, deg, left);
-                }
+                refine_fast_pred2<PA32>(xi, xaddr, xaddr + voff, low, waddr, R2r, Rmr, A, deg, left);
             }
         }
         __syncwarp();
-
-        // ---- kNN observation: obs[i, 4m:4m+4] = x_i - x_nbr(m)                                            flocking.py:20-24
-        if constexpr (KNN) {
-            int nb[TOPK];
-#pragma unroll
-            for (int m = 0; m < TOPK; ++m) nb[m] = min((int)(kp[m] & kidx), N - 1);
-            // exact order / membership among the survivors, with the reference's own keys
-            double key7 = knn_rerank(xi, i, xe, nb);
-            // Every agent with r2 <= tau was a candidate (the filter has no false negatives).  If the 7th neighbour found is
-            // itself within tau, no agent outside the candidates can be closer: done.  Otherwise (no usable hint: first step,
-            // teleported agents, a row with fewer than 7 agents in range) the warp searches all N.
-            if (!__all_sync(__activemask(), !valid || N <= KNN_K + 1 || (usable && key7 <= tau)) || N <= KNN_K + 1) {
-#pragma unroll
-                for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;
-                for (int j = 0; j < N; ++j) {
-                    if (j == i) continue;
-                    const double4 xj = xe[j];
-                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
-                    unsigned k = (__float_as_uint((float)fma(dx, dx, dy * dy)) & ~kidx) | (unsigned)j;
-#pragma unroll
-                    for (int m = 0; m < TOPK; ++m) { const unsigned lo = min(kp[m], k); k = max(kp[m], k); kp[m] = lo; }
-                }
-#pragma unroll
-                for (int m = 0; m < TOPK; ++m) nb[m] = min((int)(kp[m] & kidx), N - 1);
-                key7 = knn_rerank(xi, i, xe, nb);
-            }
-#pragma unroll
-            for (int m = 0; m < KNN_K; ++m) hint[m] = (unsigned short)nb[m];           // next step's radius comes from these
-            if (a.aux.knn_hint != nullptr && last_step && valid) {
-                uint4 hv;
-                hv.x = (unsigned)nb[0] | ((unsigned)nb[1] << 16); hv.y = (unsigned)nb[2] | ((unsigned)nb[3] << 16);
-                hv.z = (unsigned)nb[4] | ((unsigned)nb[5] << 16); hv.w = (unsigned)nb[6];
-                reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
-            }
-            if (a.obs && a.obs_direct) {
-                if (valid) {
-                    TO *o = reinterpret_cast<TO *>(a.obs) + grow * (NXS * KNN_K);
-#pragma unroll
-                    for (int m = 0; m < KNN_K; ++m) {            // the row itself / unused slots sort last: a zero block (N <= 7)
-                        const double4 xn = xe[nb[m]];
-                        if constexpr (PA32) {
-                            __stcs(reinterpret_cast<float4 *>(o) + m, make_float4((float)(xi.x - xn.x), (float)(xi.y - xn.y),
-                                                                                  (float)(xi.z - xn.z), (float)(xi.w - xn.w)));
-                        } else {
-                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m, make_double2(xi.x - xn.x, xi.y - xn.y));
-                            __stcs(reinterpret_cast<double2 *>(o) + 2 * m + 1, make_double2(xi.z - xn.z, xi.w - xn.w));
-                        }
-                    }
-                }
-            } else if (a.obs) {
-                TO *const obs_w = reinterpret_cast<TO *>(smem + a.off_obs) + (size_t)(tid - lane) * (NXS * KNN_K);
-                TO *o = obs_w + lane * (NXS * KNN_K);
-#pragma unroll
-                for (int m = 0; m < KNN_K; ++m) {
-                    const double4 xn = xe[nb[m]];
-                    o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                    o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
-                }
-                __syncwarp();
-                const int wr0 = tid - lane;                  // first row of this warp within the CTA
-                const int nrw = min(32, nrows - wr0);
-                if (nrw > 0) {
-                    const int nvec = nrw * (NXS * KNN_K) * (int)sizeof(TO) / 16;
-                    const float4 *src = reinterpret_cast<const float4 *>(obs_w);
-                    float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<TO *>(a.obs) + ((size_t)e0 * N + wr0) * (NXS * KNN_K));
-                    for (int v = lane; v < nvec; v += 32) __stcs(dst + v, src[v]);
-                }
-                __syncwarp();
-            }
-        }
 
         // ---- row epilogue: features, action, next state ----------------------------------------------------------------------
         const TO idg = inv_deg(deg, TO(0));

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a)
     const int N = a.N;
     const size_t e0 = (size_t)env * N;
     pdl_wait();
+    pdl_launch();               // the row kernel may start now: its fill warps zero the dense rows while this kernel runs
     const double4 ref = ld_state(a.x_in + e0 * 4);          // origin / reference velocity: agent 0 before the step
     const int j = b * PREP_THREADS + tid;
     double sx = 0, sy = 0, qx = 0, qy = 0;
@@ -153,7 +154,38 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
     TO *net = reinterpret_cast<TO *>(a.network);
     const int ntiles = (NP2 + a.TS - 1) / a.TS;
 
-    // ---- setup: barriers; first two tiles in flight ------------------------------------------------------------------
+    // ---- fill warps: zero the CTA's rows of the dense adjacency (one contiguous run of RTC * N elements) with coalesced
+    //      16-byte streaming stores while the other warps filter; they meet again at the block barrier before the non-zero
+    //      entries are stored.  (A filtering warp that also stores stalls on the store queue.)  They do not wait for the
+    //      prep kernel: nothing they touch depends on it, so the fill starts while prep still runs.
+    if (tid >= SW_THREADS) {
+        if (net) {
+            const int r0 = a.row_lo + blockIdx.x * RTC, r1 = min(r0 + RTC, a.row_hi);
+            if (r0 < r1) {
+                const size_t base = (e0 + r0) * (size_t)N;
+                const size_t total = (size_t)(r1 - r0) * N;
+                constexpr unsigned VEC = 16 / (unsigned)sizeof(TO);
+                const size_t headn = min((size_t)((VEC - (unsigned)(base & (VEC - 1))) & (VEC - 1)), total);
+                const size_t nvec = (total - headn) / VEC;
+                TO *out = net + base;
+                const int ft = tid - SW_THREADS, nft = blockDim.x - SW_THREADS;
+                if ((size_t)ft < headn) out[ft] = TO(0);
+                if ((size_t)ft < total - (headn + nvec * VEC)) out[headn + nvec * VEC + ft] = TO(0);
+                float4 *zdst = reinterpret_cast<float4 *>(out + headn);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                size_t v = ft;
+                for (; v + 7 * (size_t)nft < nvec; v += 8 * (size_t)nft) {     // 8 stores in flight per lane
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) __stcs(zdst + v + (size_t)q * nft, z4);
+                }
+                for (; v < nvec; v += nft) __stcs(zdst + v, z4);
+            }
+        }
+        __syncthreads();                                          // (B) the zero stores precede the non-zero stores
+        return;
+    }
+
+    // ---- setup (the 256 filtering threads): barriers, the env's totals, first two tiles in flight ---------------------------
     double *tot = reinterpret_cast<double *>(smem + a.off_tot);   // (ref vx, ref vy, sum vx, sum vy, -, ref px, ref py, -)
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     fence_async_smem();
@@ -182,38 +214,8 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
             if (a.reward && blockIdx.x == 0) reinterpret_cast<TO *>(a.reward)[env] = (TO)rew;
         }
     }
-    __syncthreads();                                              // barriers initialised, totals published
+    asm volatile("bar.sync 1, %0;" ::"n"(SW_THREADS) : "memory");  // barriers initialised, totals published
     if (tid == 0) { issue_tile(0); if (ntiles > 1) issue_tile(1); }
-
-    // ---- fill warps: zero the CTA's rows of the dense adjacency (one contiguous run of RTC * N elements) with coalesced
-    //      16-byte streaming stores while the other warps filter; they meet again at the block barrier before the non-zero
-    //      entries are stored.  (A filtering warp that also stores stalls on the store queue; measured 0.27 ms per step.)
-    if (tid >= SW_THREADS) {
-        if (net) {
-            const int r0 = a.row_lo + blockIdx.x * RTC, r1 = min(r0 + RTC, a.row_hi);
-            if (r0 < r1) {
-                const size_t base = (e0 + r0) * (size_t)N;
-                const size_t total = (size_t)(r1 - r0) * N;
-                constexpr unsigned VEC = 16 / (unsigned)sizeof(TO);
-                const size_t headn = min((size_t)((VEC - (unsigned)(base & (VEC - 1))) & (VEC - 1)), total);
-                const size_t nvec = (total - headn) / VEC;
-                TO *out = net + base;
-                const int ft = tid - SW_THREADS, nft = blockDim.x - SW_THREADS;
-                if ((size_t)ft < headn) out[ft] = TO(0);
-                if ((size_t)ft < total - (headn + nvec * VEC)) out[headn + nvec * VEC + ft] = TO(0);
-                float4 *zdst = reinterpret_cast<float4 *>(out + headn);
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                size_t v = ft;
-                for (; v + 7 * (size_t)nft < nvec; v += 8 * (size_t)nft) {     // 8 stores in flight per lane
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) __stcs(zdst + v + (size_t)q * nft, z4);
-                }
-                for (; v < nvec; v += nft) __stcs(zdst + v, z4);
-            }
-        }
-        __syncthreads();                                          // (B) the zero stores precede the non-zero stores
-        return;
-    }
 
     // ---- per-row filter state ----------------------------------------------------------------------------------------
     // Flocking-v0: the 7 nearest neighbours are searched among the candidates, so the candidate radius is inflated

@@ -140,3 +140,24 @@ def test_streaming_swarm_dense_rows_overflow_the_candidate_lists(precision, n, d
     torch.cuda.synchronize()
     check_pass(x0, sw.values.cpu().numpy(), net.cpu().numpy(), sw.u.cpu().numpy(), float(sw.reward), precision)
     check_knn_obs(obs.cpu().numpy(), x0, precision, select_kind="fp64")
+
+
+def test_swarm_graph_replay_equals_eager_steps():
+    """SwarmEnv.capture_graphs(): one CUDA graph per state parity replaces the launches of a step; same bits as eager steps."""
+    import torch
+    from gym_flock_b200 import SwarmEnv
+    from gym_flock_b200.synthetic import initial_state
+    n = 3000
+    x0 = initial_state(n, seed=12, law="density", min_dist=0.1)
+    a = SwarmEnv("Flocking-v0", n_agents=n, precision="fp32", streaming=True, distributed=False)
+    b = SwarmEnv("Flocking-v0", n_agents=n, precision="fp32", streaming=True, distributed=False)
+    a.reset(x0); b.reset(x0)
+    b.capture_graphs(warmup=2)              # (warm-up steps advance b: bring a to the same state)
+    for _ in range(2):
+        a.step()
+    for _ in range(5):
+        (oa, na), ra, _, _ = a.step()
+        (ob, nb), rb, _, _ = b.step()
+    torch.cuda.synchronize()
+    assert torch.equal(a.x, b.x) and torch.equal(a.u, b.u) and torch.equal(oa, ob) and torch.equal(na, nb) and torch.equal(ra, rb)
+    assert torch.equal(a.values, b.values)

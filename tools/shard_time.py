@@ -7,6 +7,7 @@ from gym_flock_b200 import SwarmEnv
 from gym_flock_b200.synthetic import initial_states_fast
 shard = sys.argv[1] if len(sys.argv) > 1 else "3,8"
 lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+graph = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 n = 65536
 x0 = initial_states_fast(1, n, seed=1234, law="density")[0]
 for adjacency in ("dense", "none"):
@@ -14,6 +15,8 @@ for adjacency in ("dense", "none"):
     sw = SwarmEnv("Flocking-v0", n_agents=n, precision="fp32", adjacency_mode=adjacency, distributed=False, lanes=lanes)
     del os.environ["FLOCK_EMULATE_SHARD"]
     sw.reset(x0)
+    if graph:
+        sw.capture_graphs()
     for _ in range(5):
         sw.step()
     torch.cuda.synchronize()
@@ -25,6 +28,6 @@ for adjacency in ("dense", "none"):
     ms = e0.elapsed_time(e1) / 100
     rows = sw.hi - sw.lo
     gb = rows * 4 * ((n if adjacency == "dense" else 0) + 38) / 1e9
-    print(f"shard {shard} lanes {lanes} adjacency {adjacency}: {ms*1e3:.1f} us/step  ({gb/ms*1e3:.0f} GB/s of row output)", flush=True)
+    print(f"shard {shard} lanes {lanes} graph {graph} adjacency {adjacency}: {ms*1e3:.1f} us/step  ({gb/ms*1e3:.0f} GB/s of row output)", flush=True)
     del sw
     torch.cuda.empty_cache()
