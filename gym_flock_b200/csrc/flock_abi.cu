@@ -50,7 +50,8 @@ inline int round_up32(int v) { return (v + 31) & ~31; }
 
 // diagnostics word (FlockParams.reserved): bits 0-7 CTA size / 32 of the env kernel, bits 8-15 phase switches of the env
 // kernel, bits 16-23 envs per CTA of the group kernel, bit 24 never use the group kernel, bit 25 no programmatic dependent
-// launch, bit 26 flock_rollout_* queues single-step launches instead of one fused launch
+// launch, bit 26 flock_rollout_* queues single-step launches instead of one fused launch, bit 27 stage the kNN rows in shared
+// memory, bit 28 print the device time of each kernel of a swarm step (synchronises)
 inline int tune_threads(const FlockParams *p) { return p->reserved & 0xff; }
 inline int tune_phases(const FlockParams *p) { return (p->reserved >> 8) & 0xff; }
 inline int tune_group(const FlockParams *p) { return (p->reserved >> 16) & 0xff; }
@@ -350,7 +351,7 @@ int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, doub
 }
 
 // ---- large swarms: prep kernel + streaming row kernel (flock_swarm_kernel.cuh) --------------------------------------
-struct SwarmLayout { size_t off_pf, off_partials, off_needy_cnt, off_needy, off_ovf, bytes; int NP2, PB; };
+struct SwarmLayout { size_t off_pf, off_partials, off_needy_cnt, off_needy, off_fix_d, off_fix_i, off_ticket, off_ovf, bytes; int NP2, PB; };
 
 SwarmLayout swarm_layout(int E, int N, int nrows) {
     SwarmLayout L;
@@ -360,7 +361,11 @@ SwarmLayout swarm_layout(int E, int N, int nrows) {
     L.off_partials = ((size_t)E * L.NP2 * 16 + 255) & ~(size_t)255;
     L.off_needy_cnt = L.off_partials + (((size_t)E * L.PB * 32 + 255) & ~(size_t)255);
     L.off_needy = L.off_needy_cnt + (((size_t)E * 4 + 255) & ~(size_t)255);
-    L.off_ovf = L.off_needy + (((size_t)E * flock::NEEDY_CAP * 4 + 255) & ~(size_t)255);
+    const size_t fix_entries = (size_t)E * flock::NEEDY_CAP * flock::KFIX_SPLIT * flock::TOPK;   // partial lists of the kNN fix-up
+    L.off_fix_d = L.off_needy + (((size_t)E * flock::NEEDY_CAP * 4 + 255) & ~(size_t)255);
+    L.off_fix_i = L.off_fix_d + ((fix_entries * 8 + 255) & ~(size_t)255);
+    L.off_ticket = L.off_fix_i + ((fix_entries * 4 + 255) & ~(size_t)255);
+    L.off_ovf = L.off_ticket + (((size_t)E * flock::NEEDY_CAP * 4 + 255) & ~(size_t)255);
     L.bytes = L.off_ovf + (size_t)E * nrows * 32 * flock::SW_LCAP2 * 4;       // second tier of the candidate lists
     return L;
 }
@@ -398,6 +403,9 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     a.partials = reinterpret_cast<double *>(sc + L.off_partials);
     a.needy_cnt = reinterpret_cast<unsigned *>(sc + L.off_needy_cnt);
     a.needy_rows = reinterpret_cast<unsigned *>(sc + L.off_needy);
+    a.fix_d = reinterpret_cast<double *>(sc + L.off_fix_d);
+    a.fix_i = reinterpret_cast<int *>(sc + L.off_fix_i);
+    a.fix_ticket = reinterpret_cast<unsigned *>(sc + L.off_ticket);
     a.ovf = reinterpret_cast<unsigned *>(sc + L.off_ovf);
     a.E = E; a.N = N; a.NP2 = L.NP2; a.PB = L.PB; a.row_lo = row_lo; a.row_hi = row_hi;
     a.RT = flock::SW_R * (256 / lanes);        // rows per CTA
@@ -416,7 +424,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
     // three launches, no memset: the prep kernel clears the kNN fix-up queue, the row CTAs add up its partial sums
     const bool knn = a.obs != nullptr;
     const dim3 grid((row_hi - row_lo + a.RT - 1) / a.RT, E);
-    return launch_swarm(a, (int)sizeof(T), lanes, knn, L.PB, grid, smem, st);
+    return launch_swarm(a, (int)sizeof(T), lanes, knn, L.PB, grid, smem, st, !tune_no_pdl(p), (p->reserved >> 28) & 1);
 }
 
 }  // namespace

@@ -50,7 +50,8 @@ int launch_env_f64(const flock::KArgs &k, int lanes, bool exact, bool knn, int g
 // group kernel (whole envs per CTA, `steps` fused steps)
 int launch_group(const flock::GArgs &g, int tbytes, bool knn, int grid, int threads, size_t smem, cudaStream_t st, bool pdl);
 // large swarms: prep + row kernel + kNN fix-up
-int launch_swarm(const flock::SArgs &a, int tbytes, int lanes, bool knn, int PB, dim3 grid, size_t smem, cudaStream_t st);
+int launch_swarm(const flock::SArgs &a, int tbytes, int lanes, bool knn, int PB, dim3 grid, size_t smem, cudaStream_t st, bool pdl,
+                 bool timing);
 int launch_reset(const flock::RArgs &a, size_t smem, size_t smem_cap, cudaStream_t st);
 // consumers of the adjacency bits
 int launch_aggregate(const flock::AggArgs &a, int tbytes, cudaStream_t st);

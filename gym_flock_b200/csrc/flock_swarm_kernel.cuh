@@ -36,6 +36,9 @@ struct SArgs {
     double *partials;       // scratch: [E][PB][4]  per prep block: sum (v - ref), sum (v - ref)^2
     unsigned *needy_cnt;    // scratch: [E] rows whose kNN search needs a full rescan (cleared by the prep kernel)
     unsigned *needy_rows;   // scratch: [E][NEEDY_CAP]
+    double *fix_d;          // scratch: [E][NEEDY_CAP][KFIX_SPLIT][TOPK] partial kNN lists of the fix-up kernel (r2) ...
+    int *fix_i;             //          ... and their agent indices
+    unsigned *fix_ticket;   // scratch: [E][NEEDY_CAP] arrival tickets (cleared by the prep kernel and by their last user)
     unsigned *ovf;          // scratch: [E][rows][32][SW_LCAP2] second tier of the candidate lists (touched only on overflow)
     int E, N, NP2, PB;
     int row_lo, row_hi;
@@ -49,7 +52,8 @@ struct SArgs {
 };
 
 constexpr int PREP_THREADS = 256;
-constexpr int NEEDY_CAP = 8192;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
+constexpr int NEEDY_CAP = 2048;     // rows per env the kNN fix-up kernel can take; beyond that the row kernel rescans itself
+constexpr int KFIX_SPLIT = 32;      // CTAs that share a queued row in the kNN fix-up kernel
 constexpr int SW_R = 2;         // rows per thread in the filter
 constexpr int SW_LCAP = 16;     // candidates per (row, lane) in shared memory ...
 constexpr int SW_LCAP2 = 112;   // ... and in the global second tier (dense swarms): 128 per (row, lane) before the full rescan
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(PREP_THREADS) flock_prep_kernel(const SArgs a)
         pp[0] = t0; pp[1] = t1; pp[2] = t2; pp[3] = t3;
         if (b == 0) a.needy_cnt[env] = 0u;                   // the kNN fix-up queue of this step starts empty
     }
+    if (b == 0) for (int q = tid; q < NEEDY_CAP; q += PREP_THREADS) a.fix_ticket[(size_t)env * NEEDY_CAP + q] = 0u;
 }
 
 // ---- the row kernel --------------------------------------------------------------------------------------------------
@@ -456,51 +461,102 @@ __global__ void __launch_bounds__(SW_THREADS + 32 * SW_FILL_WARPS, 2) flock_swar
     }
 }
 
-// ---- kNN fix-up: one CTA per queued row rescans all agents (exact fp64 r2, ties to the lower index) -----------------
+// ---- kNN fix-up: the queued rows rescan all agents (exact fp64 r2, ties to the lower index) ----------------------------
+// A queued row costs a full scan of the swarm, and the kernel sits on the critical path of the step (the all-gather and the
+// next prep wait for it).  One CTA per row ran the whole scan on ONE SM: ~65 us for a single queued row (the sorted insert
+// diverges, so a warp pays the full bubble whenever any lane inserts).  Now KFIX_SPLIT CTAs share a row: each scans its slice of
+// the agents, leaves its TOPK best in scratch, and the last one to arrive (a ticket per row) merges the KFIX_SPLIT lists with
+// one warp and writes the observation.  Deterministic: the merge orders by (r2, index) whatever the arrival order.
+constexpr int KFIX_THREADS = 256;
+constexpr int KFIX_SLOTS = 9;       // rows in flight: the grid is KFIX_SPLIT * KFIX_SLOTS CTAs (~2 per SM)
 template <typename TO>
-__global__ void __launch_bounds__(256) flock_knn_fix_kernel(const SArgs a) {
+__global__ void __launch_bounds__(KFIX_THREADS) flock_knn_fix_kernel(const SArgs a) {
     const int env = blockIdx.y;
     pdl_wait();
     const unsigned cnt = min(a.needy_cnt[env], (unsigned)NEEDY_CAP);
-    __shared__ double sd[8 * TOPK];
-    __shared__ int si[8 * TOPK];
+    constexpr int NW = KFIX_THREADS / 32;
+    __shared__ double sd[NW * TOPK];
+    __shared__ int si[NW * TOPK];
+    __shared__ unsigned s_last;
     const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int split = blockIdx.x % KFIX_SPLIT, slot = blockIdx.x / KFIX_SPLIT;
     const double *xc = a.x_cur + (size_t)env * N * 4;
-    for (unsigned q = blockIdx.x; q < cnt; q += gridDim.x) {
+    const int per = (N + KFIX_SPLIT - 1) / KFIX_SPLIT, j_lo = split * per, j_hi = min(N, j_lo + per);
+    auto warp_merge = [&](TopK<double> &top, const int i, double (&od)[TOPK], int (&oi)[TOPK]) {   // the warp's TOPK best, in order
+#pragma unroll
+        for (int m = 0; m < TOPK; ++m) {
+            double bd = top.d[0]; int bi = top.id[0];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const double xd = shfl_xor(bd, s); const int xi_ = shfl_xor(bi, s);
+                if (xd < bd || (xd == bd && xi_ < bi)) { bd = xd; bi = xi_; }
+            }
+            if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
+            od[m] = bd; oi[m] = bi;
+        }
+    };
+    for (unsigned q = slot; q < cnt; q += KFIX_SLOTS) {
         const int i = (int)a.needy_rows[(size_t)env * NEEDY_CAP + q];
         const double4 xi = ld_state(xc + (size_t)i * 4);
         TopK<double> top;
         top.init(i);
-        for (int j = tid; j < N; j += 256) {
-            if (j == i) continue;
-            const double2 pj = __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4));
-            const double dx = xi.x - pj.x, dy = xi.y - pj.y;
-            top.insert(fma(dx, dx, dy * dy), j);
-        }
+        // eight independent loads in flight per thread (the insert's early-out depends on the running 9th-best distance)
+        for (int j0 = j_lo + tid; j0 < j_hi; j0 += KFIX_THREADS * 8) {
+            double2 pj[8];
 #pragma unroll
-        for (int m = 0; m < TOPK; ++m) {                     // warp merge: the warp's TOPK best, in order
-            double bd = top.d[0]; int bi = top.id[0];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                const double od = shfl_xor(bd, s); const int oi = shfl_xor(bi, s);
-                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * KFIX_THREADS;
+                pj[u] = (j < j_hi) ? __ldg(reinterpret_cast<const double2 *>(xc + (size_t)j * 4)) : make_double2(CUDART_INF, CUDART_INF);
             }
-            if (bi == top.id[0] && bd == top.d[0]) top.pop_front(i);
-            if (lane == 0) { sd[warp * TOPK + m] = bd; si[warp * TOPK + m] = bi; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * KFIX_THREADS;
+                const double dx = xi.x - pj[u].x, dy = xi.y - pj[u].y;
+                if (j != i && j < j_hi) top.insert(fma(dx, dx, dy * dy), j);
+            }
+        }
+        double md[TOPK]; int mi[TOPK];
+        warp_merge(top, i, md, mi);
+        if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < TOPK; ++m) { sd[warp * TOPK + m] = md[m]; si[warp * TOPK + m] = mi[m]; }
         }
         __syncthreads();
-        if (tid == 0 && a.obs) {                             // 64 entries: one thread finishes the merge
+        double *pd = a.fix_d + (((size_t)env * NEEDY_CAP + q) * KFIX_SPLIT) * TOPK;
+        int *pi = a.fix_i + (((size_t)env * NEEDY_CAP + q) * KFIX_SPLIT) * TOPK;
+        if (warp == 0) {                                     // the CTA's TOPK best -> scratch
             TopK<double> fin;
             fin.init(i);
-            for (int e = 0; e < 8 * TOPK; ++e) if (si[e] != i) fin.insert(sd[e], si[e]);
-            knn_rerank(xi, i, reinterpret_cast<const double4 *>(xc), fin.id);
-            // equal r2: insert keeps the earlier entry in front; entries arrive in warp order, not index order
-            TO *o = reinterpret_cast<TO *>(a.obs) + ((size_t)env * N + i) * (NXS * KNN_K);
-            for (int m = 0; m < KNN_K; ++m) {
-                const double4 xn = ld_state(xc + (size_t)fin.id[m] * 4);
-                o[m * 4 + 0] = (TO)(xi.x - xn.x); o[m * 4 + 1] = (TO)(xi.y - xn.y);
-                o[m * 4 + 2] = (TO)(xi.z - xn.z); o[m * 4 + 3] = (TO)(xi.w - xn.w);
+            for (int e = lane; e < NW * TOPK; e += 32) if (si[e] != i) fin.insert(sd[e], si[e]);
+            warp_merge(fin, i, md, mi);
+            if (lane == 0) {
+#pragma unroll
+                for (int m = 0; m < TOPK; ++m) { pd[split * TOPK + m] = md[m]; pi[split * TOPK + m] = mi[m]; }
+                __threadfence();
+                s_last = (atomicAdd(a.fix_ticket + (size_t)env * NEEDY_CAP + q, 1u) == (unsigned)(KFIX_SPLIT - 1)) ? 1u : 0u;
             }
+        }
+        __syncthreads();
+        if (s_last && warp == 0) {                           // last CTA of the row: merge the KFIX_SPLIT lists, write the row
+            __threadfence();
+            TopK<double> fin;
+            fin.init(i);
+            for (int e = lane; e < KFIX_SPLIT * TOPK; e += 32) {
+                const double d = __ldcg(pd + e); const int id = __ldcg(pi + e);
+                if (id != i) fin.insert(d, id);
+            }
+            warp_merge(fin, i, md, mi);
+            knn_rerank(xi, i, reinterpret_cast<const double4 *>(xc), mi);
+            if (lane < KNN_K && a.obs) {
+                TO *o = reinterpret_cast<TO *>(a.obs) + ((size_t)env * N + i) * (NXS * KNN_K);
+                int nbm = mi[0];
+#pragma unroll
+                for (int m = 1; m < KNN_K; ++m) nbm = (lane == m) ? mi[m] : nbm;
+                const double4 xn = ld_state(xc + (size_t)nbm * 4);
+                o[lane * 4 + 0] = (TO)(xi.x - xn.x); o[lane * 4 + 1] = (TO)(xi.y - xn.y);
+                o[lane * 4 + 2] = (TO)(xi.z - xn.z); o[lane * 4 + 3] = (TO)(xi.w - xn.w);
+            }
+            if (lane == 0) a.fix_ticket[(size_t)env * NEEDY_CAP + q] = 0u;
         }
         __syncthreads();
     }

@@ -37,7 +37,7 @@ class SwarmEnv:
     def __init__(self, env_id: str = "Flocking-v0", n_agents: int = 65536, precision: str = "fp32",
                  device=None, group=None, comm_radius: float = 0.9, dt: float = 0.01, centralized: bool = True,
                  adjacency_mode: str = "dense", row_backend=None, lanes: int = 32, streaming: bool | None = None,
-                 distributed: bool | None = None):
+                 distributed: bool | None = None, tune: int = 0):
         if env_id not in _IDS:
             raise KeyError(env_id)
         self.knn = _IDS[env_id]
@@ -67,7 +67,7 @@ class SwarmEnv:
             self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
             self._params = _lib.make_params(1, self.N, comm_radius=comm_radius, dt=dt, centralized=centralized,
                                             exact=self.exact, knn_obs=self.knn, rows=(self.lo, self.hi),
-                                            lanes=1 if self.exact else lanes)
+                                            lanes=1 if self.exact else lanes, tune=tune)
             # Swarms that one CTA can stage use the env-resident kernel; larger ones (and streaming=True) the
             # streaming swarm kernel.  `lanes` is fixed (not derived from the shard size) so that every world size
             # performs bit-identical row arithmetic.
