@@ -279,14 +279,17 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         [[maybe_unused]] unsigned *mkrow = reinterpret_cast<unsigned *>(smem + a.off_masks2) + tid;
         [[maybe_unused]] unsigned short *hint = reinterpret_cast<unsigned short *>(smem + a.off_hint) + tid * 8;
         [[maybe_unused]] double tau = 0.0;
+        [[maybe_unused]] int hj[KNN_K];                      // last step's neighbours and their distances NOW (the reference's
+        [[maybe_unused]] double hk[KNN_K];                   // unfused form, the ordering key of the observation)
         if constexpr (KNN) {
 #pragma unroll
             for (int m = 0; m < KNN_K; ++m) {
-                const double4 xh = xe[min((int)hint[m], N - 1)];
-                const double dx = xi.x - xh.x, dy = xi.y - xh.y;
-                tau = fmax(tau, fma(dx, dx, dy * dy));
+                hj[m] = min((int)hint[m], N - 1);
+                const double4 xh = xe[hj[m]];
+                const double dx = __dsub_rn(xi.x, xh.x), dy = __dsub_rn(xi.y, xh.y);
+                hk[m] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                tau = fmax(tau, hk[m]);
             }
-            tau *= 1.0 + 1e-12;                              // (covers fused vs unfused rounding of the same distance)
         }
         if constexpr (PA32) {
             const int nslots = NP2;
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         } else {
             nw = (N + 31) >> 5;
             const double thrC = a.thrC;
-            [[maybe_unused]] const double thrK = tau;
+            [[maybe_unused]] const double thrK = tau * (1.0 + 1e-12);   // (fused r2 here, unfused keys in tau)
             for (int w = 0; w * 32 < N; ++w) {
                 unsigned bits = 0;
                 [[maybe_unused]] unsigned bitsk = 0;
@@ -411,9 +414,71 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             // itself within tau, no agent outside the mask can be closer: done.  Otherwise (no usable hint: first step,
             // teleported agents, N <= 8) the warp searches all N agents.
             int nb[TOPK];
+            // Fast path (nearly every row of an evolving flock): the mask holds exactly the row itself, last step's 7
+            // neighbours and at most two newcomers.  Then those <= 9 agents are the survivors -- no selection, only the exact
+            // ordering.  The check is a count: clearing the row's and the 7 hints' bits must remove exactly 8 set bits (so the
+            // hints are distinct, in range and not the row itself) and leave 0..2.
+            bool fast = false;
+            if (N > KNN_K + 1) {
+                auto mkbit = [&](const int j, const bool set) {
+                    unsigned *wp = mkrow + (j >> 5) * GMS;
+                    *wp = set ? (*wp | (1u << (j & 31))) : (*wp & ~(1u << (j & 31)));
+                };
+                mkbit(i, false);
+#pragma unroll
+                for (int m = 0; m < KNN_K; ++m) mkbit(hj[m], false);
+                int rem = 0, e0n = i, e1n = i;               // unused newcomer slots hold the row itself (sorts last)
+                for (int w = 0; w < nw; ++w) {
+                    const unsigned b = mkrow[w * GMS];
+                    const unsigned b2 = b & (b - 1);
+                    const int j0 = w * 32 + __ffs(b) - 1, j1 = w * 32 + __ffs(b2) - 1;
+                    if (rem == 0) { e0n = b ? j0 : e0n; e1n = b2 ? j1 : e1n; }
+                    else if (rem == 1) { e1n = b ? j0 : e1n; }
+                    rem += __popc(b);
+                }
+                fast = __all_sync(__activemask(), !valid || (rem == cntk - (KNN_K + 1) && rem <= TOPK - KNN_K));
+                if (fast) {
+                    double key[TOPK];
+#pragma unroll
+                    for (int m = 0; m < KNN_K; ++m) { nb[m] = hj[m]; key[m] = hk[m]; }
+                    nb[KNN_K] = e0n; nb[KNN_K + 1] = e1n;
+#pragma unroll
+                    for (int m = KNN_K; m < TOPK; ++m) {
+                        const double4 xj = xe[nb[m]];
+                        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+                        key[m] = (nb[m] == i) ? CUDART_INF : __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
+                    // last step's order with the newcomers appended is nearly sorted: odd-even transposition passes until the
+                    // warp is in order (TOPK passes always suffice; the bound also ends rows with non-finite keys)
+                    auto cx = [&](const int q) {
+                        const bool sw = key[q + 1] < key[q] || (key[q + 1] == key[q] && nb[q + 1] < nb[q]);
+                        const double ka = sw ? key[q + 1] : key[q], kb = sw ? key[q] : key[q + 1];
+                        const int ia = sw ? nb[q + 1] : nb[q], ib = sw ? nb[q] : nb[q + 1];
+                        key[q] = ka; key[q + 1] = kb; nb[q] = ia; nb[q + 1] = ib;
+                    };
+#pragma unroll 1
+                    for (int pass = 0; pass < (TOPK + 1) / 2; ++pass) {
+                        bool sorted = true;
+#pragma unroll
+                        for (int m = 0; m + 1 < TOPK; ++m)
+                            sorted = sorted && (key[m] < key[m + 1] || (key[m] == key[m + 1] && nb[m] <= nb[m + 1]));
+                        if (__all_sync(__activemask(), sorted)) break;
+#pragma unroll
+                        for (int q = 0; q + 1 < TOPK; q += 2) cx(q);
+#pragma unroll
+                        for (int q = 1; q + 1 < TOPK; q += 2) cx(q);
+                    }
+                } else {                                     // put the bits back: the search below scans the whole mask
+                    mkbit(i, true);
+#pragma unroll
+                    for (int m = 0; m < KNN_K; ++m) mkbit(hj[m], true);
+                    cntk = 0;
+                    for (int w = 0; w < nw; ++w) cntk += __popc(mkrow[w * GMS]);
+                }
+            }
             bool use_mask = __all_sync(__activemask(), !valid || cntk >= KNN_K + 1) && N > KNN_K + 1;
 #pragma unroll 1
-            for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int attempt = 0; attempt < 2 && !fast; ++attempt) {
                 if constexpr (KPACK) {
 #pragma unroll
                     for (int m = 0; m < TOPK; ++m) kp[m] = (0xFFFFFFFFu & ~kidx) | (unsigned)i;

@@ -312,3 +312,45 @@ def test_c5_giant_swarm_row_sample_vs_oracle(precision):
     assert torch.equal(part.x, sw.x) and torch.equal(prew, rew)
     assert torch.equal(part.values, sw.values[lo:hi]) and torch.equal(pobs, obs[lo:hi]) and torch.equal(pnet, net[lo:hi])
     assert torch.equal(part.u[lo:hi], sw.u[lo:hi])
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n", [100, 37, 9])
+def test_knn_observation_does_not_depend_on_the_hint(precision, n):
+    """Flocking-v0 in the group kernel: last step's neighbours (FlockAux.knn_hint) only choose the search path -- the fast
+    path (row + 7 hints + <= 2 newcomers in the radius mask), the mask search, or the scan of all N.  Garbage hints
+    (out of range, duplicates, the row itself), hints of an unrelated state (every neighbour a newcomer) and no hints give
+    the observation of the tracked run, bit for bit, and that observation is the oracle's."""
+    import torch
+    from gym_flock_b200 import FlockVecEnv
+    from gym_flock_b200.synthetic import initial_states
+    from parity_util import check_knn_obs
+    e = 6
+    x0 = initial_states(e, n, seed=5 + n, min_dist=0.1)
+    envs = {k: FlockVecEnv("Flocking-v0", num_envs=e, n_agents=n, precision=precision, lanes=1)
+            for k in ("tracked", "garbage", "foreign", "none")}
+    other = FlockVecEnv("Flocking-v0", num_envs=e, n_agents=n, precision=precision, lanes=1)
+    other.reset(initial_states(e, n, seed=900 + n, min_dist=0.1))
+    for v in envs.values():
+        v.reset(x0)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for t in range(6):
+        other.step(other.controller())
+        h = envs["garbage"]._knn_hint
+        junk = torch.randint(-32768, 32767, h.shape, generator=g, dtype=torch.int16)
+        junk[:, ::3, :] = junk[:, ::3, :1]                               # duplicates
+        junk[:, 1::5, :] = torch.arange(n, dtype=torch.int16)[1::5, None]   # the row itself
+        h.copy_(junk)
+        envs["foreign"]._knn_hint.copy_(other._knn_hint)
+        envs["none"]._knn_hint.zero_()
+        obs = {}
+        for k, v in envs.items():
+            (o, _), _, _, _ = v.step(v.controller())
+            obs[k] = o
+        torch.cuda.synchronize()
+        for k in ("garbage", "foreign", "none"):
+            assert torch.equal(envs[k].x, envs["tracked"].x), (k, t)
+            assert torch.equal(obs[k], obs["tracked"]), (k, t)
+    x = envs["tracked"].x.cpu().numpy()
+    for env in range(e):
+        check_knn_obs(obs["tracked"][env].cpu().numpy(), x[env], precision)
