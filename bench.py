@@ -314,14 +314,22 @@ def measure_env_config(D, name, cfg, rank, world, K, W, warm_ms, args, with_diag
                       adjacency_mode=args.adjacency, lanes=args.env_lanes, tune=args.tune)
     env.reset(x0)
     rewards = torch.zeros(K, E, dtype=env.dtype, device=env.device)
-    env.rollout(W)                                   # W untimed warm-up steps
+    # the time-based device warm-up evolves the flocks for thousands of steps (they spread out: fewer neighbours, cheaper
+    # steps), so the state goes back to the synthetic x0 afterwards: the K timed steps are steps W+1 .. W+K of x0
     warmed = device_warm(D, env, warm_ms) if warm_ms > 0 else 0.0
+    if warmed and not args.keep_warm_state:
+        env.reset(x0)
+    env.rollout(W)                                   # W untimed warm-up steps
     sampler = ClockSampler(D.device.index)
     sampler.start()
     ms = timed_rollout(D, env, K, rewards)           # EXACTLY K steps
     clocks = sampler.stop()
     assert bool(torch.isfinite(rewards).all()), "non-finite rewards in the timed rollout"
     assert int(env.nonfinite.sum().item()) == 0, "the kernel flagged a non-finite env"
+    # the workload the timed steps ended on: neighbours per agent (the refine phase scales with it)
+    mean_deg = None
+    if env.network is not None:
+        mean_deg = sum(int(torch.count_nonzero(env.network[e0:e0 + 256])) for e0 in range(0, E, 256)) / float(E * N)
     step_s = ms * 1e-3 / K
     alg = algorithmic_bytes(E, N, prec, knn)
     peaks, peak_src = measured_peaks()
@@ -329,7 +337,7 @@ def measure_env_config(D, name, cfg, rank, world, K, W, warm_ms, args, with_diag
     out = {"ms_per_step": ms / K, "value": world * E * N * N / step_s, "envs_per_gpu": E, "n_agents": N, "precision": prec,
            "steps": K, "algorithmic_bytes_per_step": alg, "achieved_gbs": alg / step_s / 1e9,
            "frac": alg / step_s / 1e9 / peaks["hbm_gbs"], "warmup_ms": warmed, "clocks": clocks,
-           "launches": 1 if fused else K,
+           "launches": 1 if fused else K, "mean_degree_at_end": mean_deg,
            "kernel": "flock_group_kernel (one persistent launch, K steps)" if fused else "flock_env_kernel (K launches)",
            "peak_source": peak_src}
     if with_diag:
@@ -337,9 +345,11 @@ def measure_env_config(D, name, cfg, rank, world, K, W, warm_ms, args, with_diag
         env2 = FlockVecEnv(cfg["env_id"], num_envs=E, n_agents=N, precision=prec, device=D.device,
                            adjacency_mode=args.adjacency, lanes=args.env_lanes, tune=args.tune | TUNE_NO_FUSE)
         env2.reset(x0)
-        env2.rollout(W)
         if warm_ms > 0:
             device_warm(D, env2, warm_ms)
+            if not args.keep_warm_state:
+                env2.reset(x0)
+        env2.rollout(W)
         ms2 = timed_rollout(D, env2, K)
         out["per_step_api"] = {"ms_per_step": ms2 / K, "frac": alg / (ms2 * 1e-3 / K) / 1e9 / peaks["hbm_gbs"], "launches": K,
                                "what": "the same K steps as K single-step launches (flock_step_*), queued back to back"}
@@ -612,6 +622,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                "dtype": {"fp32": "f32 pair math, f64 state", "fp64": "f64", "fp64-exact": "f64"}[prec],
                "data": "synthetic", "agent_steps_per_sec": head["value"] / N,
                "config": dict(bench_config(cfg, args.config, world), warmup_ms=head["warmup_ms"],
+                              timed_steps="steps W+1 .. W+K from the synthetic x0 (the state is reset after the device warm-up)"
+                              if not args.keep_warm_state else "the state the device warm-up left",
+                              mean_degree_at_end=head["mean_degree_at_end"],
                               step_api="flock_rollout_*: " + head["kernel"] + "; every step writes all of its outputs"),
                "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": head["frac"], "traffic": recorded_traffic(args.config), "peak_source": peak_src,
@@ -638,6 +651,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--keep-warm-state", action="store_true",
+                    help="diagnostics: time the K steps on the state the device warm-up left (default: back to x0 first)")
     ap.add_argument("--no-extras", action="store_true", help="headline config only (no per-step-API / other-config measurements)")
     ap.add_argument("--skip-gather", type=int, default=0, help="C5 diagnostic: skip the all-gather (results wrong; timing only)")
     ap.add_argument("--lanes", type=int, default=32, help="C5: threads per row of the swarm kernel (8/16/32; same on all ranks)")
