@@ -246,7 +246,7 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
         "{\n\t"                                                                                                     \
         ".reg .pred pv, pa, pg, pr;\n\t"                                                                            \
         ".reg .b32 nl, hi;\n\t"                                                                                     \
-        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c, ma, mg;\n\t"                      \
+        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c;\n\t"                      \
         "setp.ne.u32 pv, %11, 0;\n\t"                                                                            \
         "ld.shared.v2.f64 {xjx, xjy}, [%12];\n\t"                                                              \
         LD_VEL                                                                                                      \
@@ -257,25 +257,22 @@ __device__ __forceinline__ bool refine_fast(const double4 xi, const double4 xj, 
         EXTRA_BODY                                                                                                  \
         "setp.lt.and.f64 pa, r2, %18, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                        \
         "setp.le.and.f64 pg, r2, %19, pv;\n\t"  /* gradient mask: r2 <= Rm */                                     \
-        "setp.geu.and.f64 pr, r2, %18, pv;\n\t" /* a candidate that is not a neighbour */                         \
-        "selp.b32 hi, 0x3FF00000, 0, pa;\n\t"                                                                       \
-        "mov.b64 ma, {0, hi};\n\t"              /* 1.0 or 0.0 */                                                    \
-        "selp.b32 hi, 0x3FF00000, 0, pg;\n\t"                                                                       \
-        "mov.b64 mg, {0, hi};\n\t"                                                                                  \
+        "not.pred pr, pa;\n\t"                                                                                      \
+        "and.pred pr, pr, pv;\n\t"              /* a candidate that is not a neighbour */                         \
         "rcp.approx.ftz.f64 y, r2;\n\t"                                                                             \
         "neg.f64 e, r2;\n\t"                                                                                        \
         "fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\t"                                                               \
         "fma.rn.f64 y, y, c, y;\n\t"                                                                                \
         SECOND_NEWTON_STEP                                                                                          \
-        "mul.f64 ya, y, ma;\n\t"                                                                                    \
-        "mul.f64 yg, y, mg;\n\t"                                                                                    \
+        "selp.f64 ya, y, 0d0000000000000000, pa;\n\t" /* the masks as selects: y * 1.0 and y * 0.0 (y finite) */    \
+        "selp.f64 yg, y, 0d0000000000000000, pg;\n\t"                                                               \
         "mul.f64 y4, ya, ya;\n\t"                                                                                   \
         "sub.f64 dvx, %16, xjz;\n\t"                                                                             \
         "sub.f64 dvy, %17, xjw;\n\t"                                                                             \
-        "fma.rn.f64 %0, dvx, ma, %0;\n\t"                                                                     \
+        "@pa add.f64 %0, %0, dvx;\n\t"         /* = fma(dvx, 1.0, f0); + dvx * 0.0 otherwise */                  \
         "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                      \
         "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                      \
-        "fma.rn.f64 %3, dvy, ma, %3;\n\t"                                                                     \
+        "@pa add.f64 %3, %3, dvy;\n\t"                                                                         \
         "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                      \
         "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                      \
         "neg.f64 c, yg;\n\t"                                                                                        \
