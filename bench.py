@@ -80,15 +80,16 @@ def kernel_source_sha():
     return h.hexdigest()[:16]
 
 
-def recorded_traffic(name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture in profiles/traffic.json -- only if that
-    capture was taken from the kernels of this tree (source hash), else None."""
+def recorded_traffic(name, steps_per_launch=1):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu capture recorded in profiles/traffic.json (bytes per
+    step of the captured launch x the steps one launch of THIS run makes) -- only if that capture was taken from the kernels of
+    this tree (source hash), else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         if t.get("src_sha") != kernel_source_sha():
             return None
-        return t.get(name)
+        return float(t[name]["bytes_per_step"]) * steps_per_launch
     except Exception:
         return None
 
@@ -627,7 +628,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                               mean_degree_at_end=head["mean_degree_at_end"],
                               step_api="flock_rollout_*: " + head["kernel"] + "; every step writes all of its outputs"),
                "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": head["frac"], "traffic": recorded_traffic(args.config), "peak_source": peak_src,
+                            "frac": head["frac"], "traffic": recorded_traffic(args.config, K / launches), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg * K / launches, "algorithmic_bytes_per_step": alg,
                             "kernel": head["kernel"], "avg_launch_us": step_s * 1e6 * K / launches,
                             "fp_term": {"flop_per_pair": 32, "achieved_tflops": 32 * E * N * N / step_s / 1e12,
