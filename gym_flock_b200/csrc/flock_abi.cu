@@ -111,7 +111,8 @@ bool group_layout(const FlockParams *p, int tbytes, bool knn, int G, flock::GArg
     g.off_masks2 = align16((size_t)g.off_obs + (obs_staged ? (size_t)threads * flock::NXS * flock::KNN_K * tbytes : 0));
     g.off_hint = align16((size_t)g.off_masks2 + (knn ? (size_t)GMS * W * 4 : 0));
     g.obs_direct = obs_staged ? 0 : 1;
-    smem = (size_t)g.off_hint + (knn ? (size_t)threads * 16 : 0);
+    g.off_bar = align16((size_t)g.off_hint + (knn ? (size_t)threads * 16 : 0));     // the split step barrier (one mbarrier)
+    smem = (size_t)g.off_bar + 16;
     g.G = G; g.NP2 = NP2; g.W = W;
     return smem <= kMaxSmem;
 }

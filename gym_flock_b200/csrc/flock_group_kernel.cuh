@@ -44,6 +44,7 @@ struct GArgs {
     double thrC, R2, Rm, dt, inv_ascale, ulim;
     StepVariant var;
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
+    unsigned off_bar;                // the split step barrier: one mbarrier
     unsigned off_masks2, off_hint;   // Flocking-v0: kNN candidate mask (same layout as masks), last step's neighbours [T][8] u16
     unsigned xs_bytes, pf_bytes, stats_bytes;    // size of ONE copy of the parity-duplicated arrays
     int obs_direct;           // Flocking-v0: every lane stores its own observation row (7 x 16 bytes) instead of staging the
@@ -65,6 +66,81 @@ struct EnvState {
     }
     __device__ __forceinline__ EnvState operator+(const int k) const { return EnvState{p + k, v + k}; }
 };
+
+// ---- the step barrier, split into arrive and wait (an mbarrier, one arrival per warp) -------------------------------------
+// A warp ARRIVES as soon as its rows have published their next state (and it has finished reading the current one) and
+// only WAITS at the top of the next step: the expansion of its 32 dense rows -- a quarter of the step's instructions,
+// touching only the warp's own mask words -- runs while the slower warps of the CTA finish their refine loops, instead of
+// every warp idling at a block barrier behind the slowest one (the largest stall reason of the round-2 capture).
+__device__ __forceinline__ void gbar_init(unsigned long long *bar, const unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gbar_arrive(unsigned long long *bar) {       // release: the warp's shared-memory writes
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void gbar_wait(unsigned long long *bar, const unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "GBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GBAR_DONE_%=;\n\t"
+        "bra GBAR_WAIT_%=;\n"
+        "GBAR_DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// ---- refine of one candidate for a row owned by ONE thread (this kernel) ------------------------------------------------
+// Same arithmetic as refine_fast_pred2 (flock_env_kernel.cuh), but the row's mask words belong to this thread alone, so the
+// exact adjacency word is built in a register (adjw |= low when adjacent) and stored when the walk leaves the word -- no
+// shared-memory atomic per rejected candidate, no branch around it.
+template <bool NEWTON1>
+__device__ __forceinline__ void refine_group_pred(const double4 xi, const unsigned xaddr, const unsigned vaddr, const unsigned low,
+                                                  const double R2, const double Rm, Acc &A, int &deg, int &left, unsigned &adjw) {
+#define FLOCK_GROUP_REFINE_ASM(SECOND_NEWTON_STEP)                                                                  \
+    asm volatile(                                                                                                   \
+        "{\n\t"                                                                                                     \
+        ".reg .pred pv, pa, pg;\n\t"                                                                                \
+        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c;\n\t"                              \
+        "setp.ne.u32 pv, %11, 0;\n\t"                                                                               \
+        "ld.shared.v2.f64 {xjx, xjy}, [%12];\n\t"                                                                   \
+        "ld.shared.v2.f64 {xjz, xjw}, [%13];\n\t"                                                                   \
+        "sub.f64 dx, %14, xjx;\n\t"                                                                                 \
+        "sub.f64 dy, %15, xjy;\n\t"                                                                                 \
+        "mul.f64 r2, dy, dy;\n\t"                                                                                   \
+        "fma.rn.f64 r2, dx, dx, r2;\n\t"                                                                            \
+        "setp.lt.and.f64 pa, r2, %18, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                          \
+        "setp.le.and.f64 pg, r2, %19, pv;\n\t"  /* gradient mask: r2 <= Rm */                                       \
+        "rcp.approx.ftz.f64 y, r2;\n\t"                                                                             \
+        "neg.f64 e, r2;\n\t"                                                                                        \
+        "fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\t"                                                               \
+        "fma.rn.f64 y, y, c, y;\n\t"                                                                                \
+        SECOND_NEWTON_STEP                                                                                          \
+        "selp.f64 ya, y, 0d0000000000000000, pa;\n\t" /* the masks as selects: y * 1.0 and y * 0.0 (y finite) */    \
+        "selp.f64 yg, y, 0d0000000000000000, pg;\n\t"                                                               \
+        "mul.f64 y4, ya, ya;\n\t"                                                                                   \
+        "sub.f64 dvx, %16, xjz;\n\t"                                                                                \
+        "sub.f64 dvy, %17, xjw;\n\t"                                                                                \
+        "@pa add.f64 %0, %0, dvx;\n\t"                                                                              \
+        "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                            \
+        "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                            \
+        "@pa add.f64 %3, %3, dvy;\n\t"                                                                              \
+        "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                            \
+        "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                            \
+        "neg.f64 c, yg;\n\t"                                                                                        \
+        "fma.rn.f64 c, c, yg, yg;\n\t" /* 1/r2 - 1/r4 */                                                            \
+        "fma.rn.f64 %6, dx, c, %6;\n\t"                                                                             \
+        "fma.rn.f64 %7, dy, c, %7;\n\t"                                                                             \
+        "@pa add.s32 %8, %8, 1;\n\t"                                                                                \
+        "@pv add.s32 %9, %9, -1;\n\t"                                                                               \
+        "@pa or.b32 %10, %10, %11;\n\t"                                                                             \
+        "}"                                                                                                         \
+        : "+d"(A.f0), "+d"(A.f1), "+d"(A.f2), "+d"(A.f3), "+d"(A.f4), "+d"(A.f5), "+d"(A.gx), "+d"(A.gy), "+r"(deg),  \
+          "+r"(left), "+r"(adjw)                                                                                    \
+        : "r"(low), "r"(xaddr), "r"(vaddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm)            \
+        : "memory")
+    if constexpr (NEWTON1) { FLOCK_GROUP_REFINE_ASM(""); }
+    else { FLOCK_GROUP_REFINE_ASM(FLOCK_NEWTON2); }
+#undef FLOCK_GROUP_REFINE_ASM
+}
 
 // ---- in-warp expansion of 32 consecutive rows of adj_mean, N a compile-time constant ---------------------------------
 // Row r of the warp lives N elements after row r-1: with N known every store address is dst + immediate, the mask word
@@ -198,6 +274,8 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
     TO *idg_s = reinterpret_cast<TO *>(smem + a.off_idg);
     TO *net = reinterpret_cast<TO *>(a.network);
     const double R2r = a.R2, Rmr = a.Rm;
+    unsigned long long &step_bar = *reinterpret_cast<unsigned long long *>(smem + a.off_bar);   // (arrive: end of a step's epilogue)
+    if (tid == 0) gbar_init(&step_bar, blockDim.x >> 5);
 
     // ---- step-0 staging: state and action from global memory ---------------------------------------------------------------
     for (int q = tid; q < 2 * genv; q += blockDim.x)       // ready counters of both parities
@@ -235,7 +313,10 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                           reinterpret_cast<const double2 *>(smem + a.off_xs + par * a.xs_bytes + a.xs_bytes / 2)};
         const float4 *pf = reinterpret_cast<const float4 *>(smem + a.off_pf + par * a.pf_bytes);
         double *stats = reinterpret_cast<double *>(smem + a.off_stats + par * a.stats_bytes);
-        __syncthreads();                                   // the state of step t is complete; everybody left step t-1
+        // the state of step t is complete, and nobody still reads the copy this step overwrites (every warp arrived after
+        // its last read of step t-1's state)
+        if (t == 0) __syncthreads();
+        else gbar_wait(&step_bar, (unsigned)((t - 1) & 1));
 
         // ---- per-env velocity sums and reward: one warp per env, published through a step counter -----------------------
         {
@@ -263,7 +344,10 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             }
         }
 
-        if (tid - lane >= nrows) continue;                // a warp without rows (a CTA of the tail round) only keeps the barrier
+        if (tid - lane >= nrows) {                         // a warp without rows (a CTA of the tail round) only keeps the barrier
+            if (!last_step && lane == 0) gbar_arrive(&step_bar);
+            continue;
+        }
         const EnvState xe = xs + g * N;
         const double4 xi = xe[i];
         if (last_step && a.x_out && valid) st_state(a.x_out + grow * 4, xi);
@@ -569,23 +653,30 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             const unsigned voff = a.xs_bytes / 2;             // the velocity array follows the position array
             unsigned waddr = (unsigned)__cvta_generic_to_shared(mrow);
             const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 16u : 0u);
-            unsigned cand = mrow[0], nxt = mrow[GMS];         // (the mask region has one spare word row)
+            unsigned cand = valid ? mrow[0] : 0u, nxt = mrow[GMS];   // (the mask region has one spare word row)
+            unsigned adjw = 0;                                // exact adjacency bits of the word the walk is in
             int jb = 0;
             int left = valid ? cnt : 0;
-            while (left > 0) {
+            // the whole warp iterates until its busiest row is done (a lane that left the loop on its own would run the
+            // code behind it as one more divergent path); a finished lane idles on a valid address, everything predicated off
+            while (__any_sync(0xffffffffu, left > 0)) {
                 asm volatile("{\n\t.reg .pred p;\n\t"
                              "setp.eq.u32 p, %0, 0;\n\t"
+                             "setp.gt.and.s32 p, %5, 0, p;\n\t"    // (a finished row stays in its last word)
+                             "@p st.shared.u32 [%2], %4;\n\t"
+                             "@p mov.u32 %4, 0;\n\t"
                              "@p mov.u32 %0, %1;\n\t"
-                             "@p add.u32 %2, %2, %4;\n\t"
+                             "@p add.u32 %2, %2, %6;\n\t"
                              "@p add.s32 %3, %3, 32;\n\t"
-                             "@p ld.shared.u32 %1, [%2+%4];\n\t}"
-                             : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(jb) : "n"(GMS * 4) : "memory");
+                             "@p ld.shared.u32 %1, [%2+%6];\n\t}"
+                             : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(jb), "+r"(adjw) : "r"(left), "n"(GMS * 4) : "memory");
                 const unsigned low = cand & (0u - cand);
                 cand ^= low;
                 const int j = jb + bfind(low);
                 const unsigned xaddr = low ? xe_s + (unsigned)j * 16u : xdummy;
-                refine_fast_pred2<PA32>(xi, xaddr, xaddr + voff, low, waddr, R2r, Rmr, A, deg, left);
+                refine_group_pred<PA32>(xi, xaddr, xaddr + voff, low, R2r, Rmr, A, deg, left, adjw);
             }
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(waddr), "r"(adjw) : "memory");    // the last word visited
         }
         __syncwarp();
 
@@ -683,8 +774,9 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         }
 
         // ---- dense adj_mean rows: every warp expands its own 32 rows from their exact bit masks -------------------------------
+        __syncwarp();                                        // the lanes' next state, mask words and 1/deg (shared memory) are complete
+        if (!last_step && lane == 0) gbar_arrive(&step_bar);
         if (net != nullptr) {
-            __syncwarp();                                    // the lanes' mask words and 1/deg (shared memory) are complete
             const int wr0 = tid - lane;
             const int nrw = min(32, nrows - wr0);
             if (nrw > 0) {
