@@ -94,21 +94,21 @@ __device__ __forceinline__ void gbar_wait(unsigned long long *bar, const unsigne
 // shared-memory atomic per rejected candidate, no branch around it.
 template <bool NEWTON1>
 __device__ __forceinline__ void refine_group_pred(const double4 xi, const unsigned xaddr, const unsigned vaddr, const unsigned low,
-                                                  const double R2, const double Rm, Acc &A, int &deg, int &left, unsigned &adjw) {
+                                                  const double R2, const double Rm, Acc &A, int &deg, unsigned &adjw) {
 #define FLOCK_GROUP_REFINE_ASM(SECOND_NEWTON_STEP)                                                                  \
     asm volatile(                                                                                                   \
         "{\n\t"                                                                                                     \
         ".reg .pred pv, pa, pg;\n\t"                                                                                \
-        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c;\n\t"                              \
-        "setp.ne.u32 pv, %11, 0;\n\t"                                                                               \
-        "ld.shared.v2.f64 {xjx, xjy}, [%12];\n\t"                                                                   \
-        "ld.shared.v2.f64 {xjz, xjw}, [%13];\n\t"                                                                   \
-        "sub.f64 dx, %14, xjx;\n\t"                                                                                 \
-        "sub.f64 dy, %15, xjy;\n\t"                                                                                 \
+        ".reg .f64 xjx, xjy, xjz, xjw, dx, dy, r2, y, e, ya, y4, yg, dvx, dvy, c, ma;\n\t"                          \
+        "setp.ne.u32 pv, %10, 0;\n\t"                                                                               \
+        "ld.shared.v2.f64 {xjx, xjy}, [%11];\n\t"                                                                   \
+        "ld.shared.v2.f64 {xjz, xjw}, [%12];\n\t"                                                                   \
+        "sub.f64 dx, %13, xjx;\n\t"                                                                                 \
+        "sub.f64 dy, %14, xjy;\n\t"                                                                                 \
         "mul.f64 r2, dy, dy;\n\t"                                                                                   \
         "fma.rn.f64 r2, dx, dx, r2;\n\t"                                                                            \
-        "setp.lt.and.f64 pa, r2, %18, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                          \
-        "setp.le.and.f64 pg, r2, %19, pv;\n\t"  /* gradient mask: r2 <= Rm */                                       \
+        "setp.lt.and.f64 pa, r2, %17, pv;\n\t"  /* adjacency: r2 < R^2 (squared radius) */                          \
+        "setp.le.and.f64 pg, r2, %18, pv;\n\t"  /* gradient mask: r2 <= Rm */                                       \
         "rcp.approx.ftz.f64 y, r2;\n\t"                                                                             \
         "neg.f64 e, r2;\n\t"                                                                                        \
         "fma.rn.f64 c, e, y, 0d3FF0000000000000;\n\t"                                                               \
@@ -117,12 +117,13 @@ __device__ __forceinline__ void refine_group_pred(const double4 xi, const unsign
         "selp.f64 ya, y, 0d0000000000000000, pa;\n\t" /* the masks as selects: y * 1.0 and y * 0.0 (y finite) */    \
         "selp.f64 yg, y, 0d0000000000000000, pg;\n\t"                                                               \
         "mul.f64 y4, ya, ya;\n\t"                                                                                   \
-        "sub.f64 dvx, %16, xjz;\n\t"                                                                                \
-        "sub.f64 dvy, %17, xjw;\n\t"                                                                                \
-        "@pa add.f64 %0, %0, dvx;\n\t"                                                                              \
+        "sub.f64 dvx, %15, xjz;\n\t"                                                                                \
+        "sub.f64 dvy, %16, xjw;\n\t"                                                                                \
+        "selp.f64 ma, 0d3FF0000000000000, 0d0000000000000000, pa;\n\t"                                              \
+        "fma.rn.f64 %0, dvx, ma, %0;\n\t"     /* + dvx * 1.0 / + dvx * 0.0: exact (dvx finite) */                    \
         "fma.rn.f64 %1, dx, y4, %1;\n\t"                                                                            \
         "fma.rn.f64 %2, dx, ya, %2;\n\t"                                                                            \
-        "@pa add.f64 %3, %3, dvy;\n\t"                                                                              \
+        "fma.rn.f64 %3, dvy, ma, %3;\n\t"                                                                           \
         "fma.rn.f64 %4, dy, y4, %4;\n\t"                                                                            \
         "fma.rn.f64 %5, dy, ya, %5;\n\t"                                                                            \
         "neg.f64 c, yg;\n\t"                                                                                        \
@@ -130,11 +131,10 @@ __device__ __forceinline__ void refine_group_pred(const double4 xi, const unsign
         "fma.rn.f64 %6, dx, c, %6;\n\t"                                                                             \
         "fma.rn.f64 %7, dy, c, %7;\n\t"                                                                             \
         "@pa add.s32 %8, %8, 1;\n\t"                                                                                \
-        "@pv add.s32 %9, %9, -1;\n\t"                                                                               \
-        "@pa or.b32 %10, %10, %11;\n\t"                                                                             \
+        "@pa or.b32 %9, %9, %10;\n\t"                                                                               \
         "}"                                                                                                         \
         : "+d"(A.f0), "+d"(A.f1), "+d"(A.f2), "+d"(A.f3), "+d"(A.f4), "+d"(A.f5), "+d"(A.gx), "+d"(A.gy), "+r"(deg),  \
-          "+r"(left), "+r"(adjw)                                                                                    \
+          "+r"(adjw)                                                                                               \
         : "r"(low), "r"(xaddr), "r"(vaddr), "d"(xi.x), "d"(xi.y), "d"(xi.z), "d"(xi.w), "d"(R2), "d"(Rm)            \
         : "memory")
     if constexpr (NEWTON1) { FLOCK_GROUP_REFINE_ASM(""); }
@@ -358,7 +358,17 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         // farthest of ANY 7 agents); neighbourhoods change slowly, so that mask holds 7-10 agents instead of N.  The hint
         // only sets the radius: stale, missing or garbage hints cost time (a mask with < 7 agents falls back to all N),
         // never correctness.
-        int cnt = 0, cntk = 0;
+        // cnt: candidates of the row WITHOUT the diagonal (r2 = 0 is always a candidate; +inf in the reference, :115 -- its bit is
+        // cleared before the word is stored); idle: iterations the refine walk spends on empty words (every empty word after
+        // word 0 and before the row's last non-empty word costs it one)
+        int cnt = 0, cntk = 0, idle = 0, empties = 0;
+        const int diag_w = i >> 5;
+        const unsigned diag_m = ~(1u << (i & 31));
+        auto count_word = [&](const int w, const unsigned bits) {
+            cnt += __popc(bits);
+            idle = bits ? empties : idle;
+            empties += (w >= 1 && bits == 0u) ? 1 : 0;
+        };
         int nw;
         [[maybe_unused]] unsigned *mkrow = reinterpret_cast<unsigned *>(smem + a.off_masks2) + tid;
         [[maybe_unused]] unsigned short *hint = reinterpret_cast<unsigned short *>(smem + a.off_hint) + tid * 8;
@@ -422,8 +432,9 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                     bits = __brev(bits) >> (32 - 2 * tend);          // 0 < tend <= 16
                     if constexpr (KNN) bitsk = __brev(bitsk) >> (32 - 2 * tend);
                 }
+                bits &= (w == diag_w) ? diag_m : 0xffffffffu;
                 mrow[w * GMS] = bits;
-                cnt += __popc(bits);
+                count_word(w, bits);
                 if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
             };
             if constexpr (NC != 0) {
@@ -461,8 +472,9 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 } else {
                     for (int kk = 0; kk < kend; ++kk) body(kk);
                 }
+                bits &= (w == diag_w) ? diag_m : 0xffffffffu;
                 mrow[w * GMS] = bits;
-                cnt += __popc(bits);
+                count_word(w, bits);
                 if constexpr (KNN) { mkrow[w * GMS] = bitsk; cntk += __popc(bitsk); }
             }
         }
@@ -646,35 +658,42 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         A.f0 = A.f1 = A.f2 = A.f3 = A.f4 = A.f5 = A.gx = A.gy = A.s0 = A.s1 = 0.0;
         int deg = 0;
         {
-            // the diagonal (r2 = 0: always a candidate; +inf in the reference, :115) is removed up front
-            mrow[(i >> 5) * GMS] &= ~(1u << (i & 31));
-            --cnt;
+            // The walk: `cand` holds the unvisited candidates of the current word, `xbase` the shared-memory address of that
+            // word's first agent, `adjw` the exact adjacency bits found in it (stored when the walk leaves the word: the row's
+            // words belong to this thread alone).  The whole warp runs max-over-lanes(cnt + idle) iterations of straight-line
+            // code -- a counted, warp-uniform loop: no vote, no divergent exit; a lane that has run out idles on the
+            // word's first agent with everything selected off (that agent may be the row itself: r2 = 0 gives a non-finite
+            // reciprocal, which only ever feeds selects).
             const unsigned xe_s = (unsigned)__cvta_generic_to_shared(xe.p);
             const unsigned voff = a.xs_bytes / 2;             // the velocity array follows the position array
             unsigned waddr = (unsigned)__cvta_generic_to_shared(mrow);
-            const unsigned xdummy = xe_s + ((i == 0 && N > 1) ? 16u : 0u);
+            const unsigned wlast = waddr + (unsigned)(nw - 1) * (GMS * 4);
             unsigned cand = valid ? mrow[0] : 0u, nxt = mrow[GMS];   // (the mask region has one spare word row)
-            unsigned adjw = 0;                                // exact adjacency bits of the word the walk is in
-            int jb = 0;
-            int left = valid ? cnt : 0;
-            // the whole warp iterates until its busiest row is done (a lane that left the loop on its own would run the
-            // code behind it as one more divergent path); a finished lane idles on a valid address, everything predicated off
-            while (__any_sync(0xffffffffu, left > 0)) {
+            unsigned adjw = 0;
+            unsigned xbase = xe_s;
+            const int niter = __reduce_max_sync(0xffffffffu, valid ? cnt + idle : 0);
+#pragma unroll 1
+            for (int it = 0; it < niter; ++it) {
                 asm volatile("{\n\t.reg .pred p;\n\t"
                              "setp.eq.u32 p, %0, 0;\n\t"
-                             "setp.gt.and.s32 p, %5, 0, p;\n\t"    // (a finished row stays in its last word)
+                             "setp.lt.and.u32 p, %2, %5, p;\n\t"   // (the walk ends in the row's last word)
                              "@p st.shared.u32 [%2], %4;\n\t"
                              "@p mov.u32 %4, 0;\n\t"
                              "@p mov.u32 %0, %1;\n\t"
                              "@p add.u32 %2, %2, %6;\n\t"
-                             "@p add.s32 %3, %3, 32;\n\t"
+                             "@p add.u32 %3, %3, 512;\n\t"
                              "@p ld.shared.u32 %1, [%2+%6];\n\t}"
-                             : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(jb), "+r"(adjw) : "r"(left), "n"(GMS * 4) : "memory");
-                const unsigned low = cand & (0u - cand);
-                cand ^= low;
-                const int j = jb + bfind(low);
-                const unsigned xaddr = low ? xe_s + (unsigned)j * 16u : xdummy;
-                refine_group_pred<PA32>(xi, xaddr, xaddr + voff, low, R2r, Rmr, A, deg, left, adjw);
+                             : "+r"(cand), "+r"(nxt), "+r"(waddr), "+r"(xbase), "+r"(adjw) : "r"(wlast), "n"(GMS * 4) : "memory");
+                unsigned low, xaddr;        // lowest candidate of the word and its agent (a lane without one: the word's first agent)
+                asm volatile("{\n\t.reg .b32 t;\n\t"
+                             "neg.s32 t, %0;\n\t"
+                             "and.b32 %1, %0, t;\n\t"
+                             "xor.b32 %0, %0, %1;\n\t"
+                             "or.b32 t, %1, 1;\n\t"
+                             "bfind.u32 t, t;\n\t"
+                             "mad.lo.u32 %2, t, 16, %3;\n\t}"
+                             : "+r"(cand), "=r"(low), "=r"(xaddr) : "r"(xbase));
+                refine_group_pred<PA32>(xi, xaddr, xaddr + voff, low, R2r, Rmr, A, deg, adjw);
             }
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(waddr), "r"(adjw) : "memory");    // the last word visited
         }
