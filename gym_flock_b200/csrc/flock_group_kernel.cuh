@@ -79,13 +79,26 @@ __device__ __forceinline__ void gbar_arrive(unsigned long long *bar) {       // 
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void gbar_wait(unsigned long long *bar, const unsigned parity) {
+    // try_wait suspends the warp in hardware for up to the time hint before it answers "not yet": a waiting warp must not
+    // spend issue slots polling (without the hint the polling loop was 12 % of the executed instructions of a step)
+#ifndef FLOCK_GBAR_SLEEP
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "GBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra GBAR_DONE_%=;\n\t"
+        "bra GBAR_WAIT_%=;\n"
+        "GBAR_DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity), "r"(0x989680u) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n"
         "GBAR_WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra GBAR_DONE_%=;\n\t"
+        "nanosleep.u32 %2;\n\t"
         "bra GBAR_WAIT_%=;\n"
-        "GBAR_DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+        "GBAR_DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity), "n"(FLOCK_GBAR_SLEEP) : "memory");
+#endif
 }
 
 // ---- refine of one candidate for a row owned by ONE thread (this kernel) ------------------------------------------------
@@ -376,9 +389,11 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
         [[maybe_unused]] int hj[KNN_K];                      // last step's neighbours and their distances NOW (the reference's
         [[maybe_unused]] double hk[KNN_K];                   // unfused form, the ordering key of the observation)
         if constexpr (KNN) {
+            const uint4 hv4 = *reinterpret_cast<const uint4 *>(hint);      // 8 x u16 in one 16-byte load (no bank conflicts)
+            const unsigned hw[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
 #pragma unroll
             for (int m = 0; m < KNN_K; ++m) {
-                hj[m] = min((int)hint[m], N - 1);
+                hj[m] = min((int)((hw[m >> 1] >> ((m & 1) * 16)) & 0xffffu), N - 1);
                 const double4 xh = xe[hj[m]];
                 const double dx = __dsub_rn(xi.x, xh.x), dy = __dsub_rn(xi.y, xh.y);
                 hk[m] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
@@ -609,12 +624,12 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 use_mask = false;
             }
 #pragma unroll
-            for (int m = 0; m < KNN_K; ++m) hint[m] = (unsigned short)nb[m];           // next step's radius comes from these
-            if (a.aux.knn_hint != nullptr && last_step && valid) {
+            {                                                // next step's radius comes from these
                 uint4 hv;
                 hv.x = (unsigned)nb[0] | ((unsigned)nb[1] << 16); hv.y = (unsigned)nb[2] | ((unsigned)nb[3] << 16);
                 hv.z = (unsigned)nb[4] | ((unsigned)nb[5] << 16); hv.w = (unsigned)nb[6];
-                reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
+                *reinterpret_cast<uint4 *>(hint) = hv;
+                if (a.aux.knn_hint != nullptr && last_step && valid) reinterpret_cast<uint4 *>(a.aux.knn_hint)[grow] = hv;
             }
             if (a.obs && a.obs_direct) {
                 if (valid) {
