@@ -176,6 +176,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.mark_t, self.stamps = None, []          # mark(): start of the timed region (samples after it are counted apart)
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -192,19 +193,27 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.stamps.append(time.perf_counter())
                 r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 for bit, name in self.REASONS.items():
                     if r & bit and name != "gpu_idle":
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0005)
+
+    def mark(self):
+        self.mark_t = time.perf_counter()
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.mark_t is not None:      # the sampler ran from the device warm-up (same kernel, same load) through the timed region
+            out["samples_in_timed_region"] = sum(1 for t in self.stamps if t >= self.mark_t)
+            out["window"] = "device warm-up + W warm-up steps + the K timed steps (one continuous load)"
+        return out
 
 
 # ---- arms ------------------------------------------------------------------------------------------------------------
@@ -317,12 +326,15 @@ def measure_env_config(D, name, cfg, rank, world, K, W, warm_ms, args, with_diag
     rewards = torch.zeros(K, E, dtype=env.dtype, device=env.device)
     # the time-based device warm-up evolves the flocks for thousands of steps (they spread out: fewer neighbours, cheaper
     # steps), so the state goes back to the synthetic x0 afterwards: the K timed steps are steps W+1 .. W+K of x0
+    # a short run's timed region (K = 20: under 1 ms) is shorter than one NVML query, so the sampler covers the continuous load
+    # from the device warm-up on and counts the samples that fell into the timed region separately
+    sampler = ClockSampler(D.device.index)
+    sampler.start()
     warmed = device_warm(D, env, warm_ms) if warm_ms > 0 else 0.0
     if warmed and not args.keep_warm_state:
         env.reset(x0)
     env.rollout(W)                                   # W untimed warm-up steps
-    sampler = ClockSampler(D.device.index)
-    sampler.start()
+    sampler.mark()
     ms = timed_rollout(D, env, K, rewards)           # EXACTLY K steps
     clocks = sampler.stop()
     assert bool(torch.isfinite(rewards).all()), "non-finite rewards in the timed rollout"

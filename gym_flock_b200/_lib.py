@@ -15,7 +15,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("FLOCK_LIB") or os.path.join(_PKG, "libflock_b200.so")
 # translation units (compiled in parallel, then linked) and the headers they depend on
-_UNITS = ("flock_abi.cu", "launch_env_f32.cu", "launch_env_f64.cu", "launch_group.cu", "launch_swarm.cu", "launch_graph.cu")
+_UNITS = ("flock_abi.cu", "launch_env_f32.cu", "launch_env_f64.cu", "launch_group.cu", "launch_swarm.cu", "launch_graph.cu",
+          "nvtx_ranges.cu")
 _HEADERS = ("flock_host.hpp", "flock_common.cuh", "flock_env_kernel.cuh", "flock_group_kernel.cuh", "flock_swarm_kernel.cuh",
             "flock_reset_kernel.cuh", "flock_graph_kernels.cuh")
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in _UNITS + _HEADERS] + [os.path.join(_ROOT, "include", "flock_b200.h")]
@@ -86,7 +87,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
 
     with ThreadPoolExecutor(max_workers=len(_UNITS)) as pool:
         objs = list(pool.map(compile_unit, _UNITS))
-    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, check=True)
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-ldl"], check=True)   # (-ldl: NVTX v3)
     return out
 
 

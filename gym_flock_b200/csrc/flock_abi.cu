@@ -302,6 +302,7 @@ template <typename T>
 int step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
               T *reward, double *u_next, T *obs, const FlockAux *aux, void *stream, int steps = 1, T *rewards_all = nullptr,
               bool *fused = nullptr) {
+    NvtxRange nvtx_("flock_step");
     Plan pl;
     int rc = make_plan(p, (int)sizeof(T), pl, aux && aux->adj_bits);
     if (rc) return rc;
@@ -331,6 +332,7 @@ int step_impl(const FlockParams *p, const double *x_in, const double *u_in, doub
 template <typename T>
 int rollout_impl(const FlockParams *p, int steps, double *x_a, double *x_b, double *u_a, double *u_b, T *values,
                  T *network, T *reward, T *rewards_all, T *obs, int32_t *final_in_b, void *stream) {
+    NvtxRange nvtx_("flock_rollout");
     if (steps < 0) return fail(FLOCK_EINVAL, "steps=%d", steps);
     if (!x_a || !x_b || !u_a || !u_b) return fail(FLOCK_EINVAL, "x_a/x_b/u_a/u_b must be non-NULL");
     if (final_in_b) *final_in_b = (steps & 1);
@@ -378,6 +380,7 @@ SwarmLayout swarm_layout(int E, int N, int nrows) {
 template <typename T>
 int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in, double *x_out, T *values, T *network,
                     T *reward, double *u_next, T *obs, void *scratch, size_t scratch_bytes, void *stream) {
+    NvtxRange nvtx_("flock_swarm_step");
     if (!p) return fail(FLOCK_EINVAL, "params is NULL");
     const int E = p->n_envs, N = p->n_agents;
     if (E < 1 || N < 2) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d", E, N);
@@ -436,6 +439,7 @@ int swarm_step_impl(const FlockParams *p, const double *x_in, const double *u_in
 
 int reset_sample_impl(const FlockParams *p, double r_max, double v_max, double v_bias, double min_dist, uint64_t seed,
                       int32_t max_tries, double *x_out, int32_t *tries_out, void *stream) {
+    NvtxRange nvtx_("flock_reset_sample");
     if (!p) return fail(FLOCK_EINVAL, "params is NULL");
     const int E = p->n_envs, N = p->n_agents;
     if (E < 1 || N < 1) return fail(FLOCK_EINVAL, "n_envs=%d n_agents=%d must be >= 1", E, N);
@@ -673,6 +677,7 @@ int flock_ctx_set_params(FlockCtx *c, const FlockParams *p) {
 
 int flock_ctx_set_state(FlockCtx *c, const double *x_host, void *values_host, void *network_host, void *reward_host,
                         void *obs_host) {
+    NvtxRange nvtx_("flock_ctx_set_state");
     if (!c || !x_host) return fail(FLOCK_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(c->x[c->cur], x_host, n_x(c) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -693,6 +698,7 @@ int flock_ctx_upload_state(FlockCtx *c, const double *x_host) {
 
 int flock_ctx_step(FlockCtx *c, const double *u_host, void *values_host, void *network_host, void *reward_host,
                    void *obs_host) {
+    NvtxRange nvtx_("flock_ctx_step");
     if (!c) return fail(FLOCK_EINVAL, "NULL context");
     CUDA_TRY(cudaSetDevice(c->device));
     if (u_host) {
@@ -710,6 +716,7 @@ int flock_ctx_step(FlockCtx *c, const double *u_host, void *values_host, void *n
 }
 
 int flock_ctx_controller(FlockCtx *c, int32_t centralized, double *u_host) {
+    NvtxRange nvtx_("flock_ctx_controller");
     if (!c || !u_host) return fail(FLOCK_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(c->device));
     const int want = centralized ? FLOCK_CENTRALIZED : 0;
@@ -735,6 +742,7 @@ int flock_ctx_get_state(FlockCtx *c, double *x_host) {
 }
 
 int flock_ctx_get_stats(FlockCtx *c, void *vel_diffs_host, void *min_dists_host) {
+    NvtxRange nvtx_("flock_ctx_get_stats");
     if (!c) return fail(FLOCK_EINVAL, "NULL context");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t bytes = (size_t)c->p.n_envs * c->p.n_agents * c->tbytes;

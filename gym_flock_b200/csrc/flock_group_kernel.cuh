@@ -623,7 +623,6 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                 if (!use_mask || __all_sync(__activemask(), !valid || key7 <= tau)) break;
                 use_mask = false;
             }
-#pragma unroll
             {                                                // next step's radius comes from these
                 uint4 hv;
                 hv.x = (unsigned)nb[0] | ((unsigned)nb[1] << 16); hv.y = (unsigned)nb[2] | ((unsigned)nb[3] << 16);

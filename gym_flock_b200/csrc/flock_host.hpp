@@ -26,6 +26,17 @@ int flock_fail(int code, const char *fmt, ...);
         if (e_ != cudaSuccess) return flock_fail(FLOCK_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));  \
     } while (0)
 
+// NVTX range over one entry point of the C ABI (shows up as a named span in nsys / ncu timelines)
+// (nvtx_ranges.cu: the NVTX header pulls in POSIX flock(), which cannot share a translation unit with namespace flock)
+void flock_nvtx_push(const char *name);
+void flock_nvtx_pop();
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { flock_nvtx_push(name); }
+    ~NvtxRange() { flock_nvtx_pop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 constexpr int kSMs = 148;
 constexpr size_t kMaxSmem = 227 * 1024;
 
