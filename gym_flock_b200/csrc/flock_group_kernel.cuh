@@ -262,7 +262,10 @@ __device__ __forceinline__ void expand_rows_g(TO *wout, const unsigned *wm, cons
 }
 
 template <typename TO, bool KNN, int NC, int GMS>
-__global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
+#ifndef FLOCK_GROUP_MINB
+#define FLOCK_GROUP_MINB 2
+#endif
+__global__ void __launch_bounds__(GMAXT, FLOCK_GROUP_MINB) flock_group_kernel(const GArgs a) {
     constexpr bool PA32 = std::is_same<TO, float>::value;
     using TK = typename std::conditional<PA32, float, double>::type;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -686,8 +689,7 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
             unsigned adjw = 0;
             unsigned xbase = xe_s;
             const int niter = __reduce_max_sync(0xffffffffu, valid ? cnt + idle : 0);
-#pragma unroll 1
-            for (int it = 0; it < niter; ++it) {
+            auto walk_step = [&]() {
                 asm volatile("{\n\t.reg .pred p;\n\t"
                              "setp.eq.u32 p, %0, 0;\n\t"
                              "setp.lt.and.u32 p, %2, %5, p;\n\t"   // (the walk ends in the row's last word)
@@ -708,7 +710,17 @@ __global__ void __launch_bounds__(GMAXT, 2) flock_group_kernel(const GArgs a) {
                              "mad.lo.u32 %2, t, 16, %3;\n\t}"
                              : "+r"(cand), "=r"(low), "=r"(xaddr) : "r"(xbase));
                 refine_group_pred<PA32>(xi, xaddr, xaddr + voff, low, R2r, Rmr, A, deg, adjw);
+            };
+            // two candidates per iteration, in order: the loads and reciprocals of the pair overlap (the sums stay sequential, so
+            // the result does not change), an odd count ends with a single step
+            // (Flocking-v0 keeps one per iteration: its register budget is spent on the kNN state, the pair only adds spills)
+            int it = 0;
+            if constexpr (!KNN) {
+#pragma unroll 1
+                for (; it + 2 <= niter; it += 2) { walk_step(); walk_step(); }
             }
+#pragma unroll 1
+            for (; it < niter; ++it) walk_step();
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(waddr), "r"(adjw) : "memory");    // the last word visited
         }
         __syncwarp();
