@@ -709,39 +709,62 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
     } else {
         nk = valid ? (N - sub + LANES - 1) / LANES : 0;
         const double thrC = a.thrC;
-        for (int w = 0; w * 32 < nk; ++w) {
-            unsigned bits = 0;
-            const int kbase = w * 32;
-            const int kend = min(32, nk - kbase);
-            auto body = [&](const int kk) {
-                const int j = sub + LANES * (kbase + kk);
-                const double4 xj = xe[j];
-                double r2;
-                bool c;
-                if constexpr (EXACT) {
-                    const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
-                    r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    c = (r2 < a.R2) || !(r2 > a.R);
-                    if (cen && !(i < nobs || j < nobs)) {   // sum_j (v_i - v_j) over ALL j, sequential (flocking_relative.py:204-208);
-                        A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));   // obstacle rows / columns contribute exact zeros
-                        A.s1 = __dadd_rn(A.s1, __dsub_rn(xi.w, xj.w));
+        [[maybe_unused]] const double thrX = (a.R2 <= a.R) ? a.R : __longlong_as_double(__double_as_longlong(a.R2) - 1);   // (R^2 > 0)
+        // EXACT, centralized: the alignment sums run over ALL j in order (flocking_relative.py:204-208).  The obstacle test
+        // (rows / columns of obstacles contribute exact zeros) is per pair only when the env has obstacles: three loop variants
+        // picked by one warp-uniform branch.  SUMS 0: no sums (decentralized / fast modes), 1: every pair, 2: per-pair test.
+        auto words = [&](auto SUMS) {
+            [[maybe_unused]] constexpr int SM = decltype(SUMS)::value;
+            for (int w = 0; w * 32 < nk; ++w) {
+                unsigned bits = 0;
+                const int kbase = w * 32;
+                const int kend = min(32, nk - kbase);
+                auto body = [&](const int kk) {
+                    const int j = sub + LANES * (kbase + kk);
+                    const double4 xj = xe[j];
+                    double r2;
+                    [[maybe_unused]] bool c;
+                    if constexpr (EXACT) {
+                        const double dx = __dsub_rn(xi.x, xj.x), dy = __dsub_rn(xi.y, xj.y);
+                        r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        // candidate = (r2 < R^2) || !(r2 > R), the union of the two masks refine_exact applies: one compare,
+                        // !(r2 > thrX) with thrX = R if R^2 <= R, else the double just below R^2 (NaN stays a candidate);
+                        // the bit is one predicated OR
+                        asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@!p or.b32 %0, %0, %3;\n\t}"
+                            : "+r"(bits) : "d"(r2), "d"(thrX), "r"(1u << kk));
+                        if (SM == 1 || (SM == 2 && !(i < nobs || j < nobs))) {
+                            A.s0 = __dadd_rn(A.s0, __dsub_rn(xi.z, xj.z));
+                            A.s1 = __dadd_rn(A.s1, __dsub_rn(xi.w, xj.w));
+                        }
+                    } else {
+                        const double dx = xi.x - xj.x, dy = xi.y - xj.y;
+                        r2 = fma(dx, dx, dy * dy);
+                        c = r2 <= thrC;
+                        bits |= c ? (1u << kk) : 0u;
+                    }
+                    if constexpr (KNN) top.insert(r2, j);
+                };
+                if (kend == 32) {
+                    if constexpr (EXACT) {
+#pragma unroll
+                        for (int kk = 0; kk < 32; ++kk) body(kk);
+                    } else {
+#pragma unroll 8
+                        for (int kk = 0; kk < 32; ++kk) body(kk);
                     }
                 } else {
-                    const double dx = xi.x - xj.x, dy = xi.y - xj.y;
-                    r2 = fma(dx, dx, dy * dy);
-                    c = r2 <= thrC;
+                    for (int kk = 0; kk < kend; ++kk) body(kk);
                 }
-                bits |= c ? (1u << kk) : 0u;
-                if constexpr (KNN) top.insert(r2, j);
-            };
-            if (kend == 32) {
-#pragma unroll 8
-                for (int kk = 0; kk < 32; ++kk) body(kk);
-            } else {
-                for (int kk = 0; kk < kend; ++kk) body(kk);
+                mrow[w * MS] = bits;
+                cnt += __popc(bits);
             }
-            mrow[w * MS] = bits;
-            cnt += __popc(bits);
+        };
+        if constexpr (EXACT) {
+            if (!cen) words(std::integral_constant<int, 0>{});
+            else if (nobs == 0) words(std::integral_constant<int, 1>{});
+            else words(std::integral_constant<int, 2>{});
+        } else {
+            words(std::integral_constant<int, 0>{});
         }
     }
     const int nw = (nk + 31) >> 5;
@@ -1059,8 +1082,11 @@ __device__ __forceinline__ void expand_window(TO *network, const int N, const in
 // Resident-CTA targets: the fast kernels are latency bound (divergent refine loops), so occupancy matters more than
 // registers: 256-thread bound, FLOCK_MINB CTAs per SM.  EXACT keeps its registers.
 // One CTA = one window.
+#ifndef FLOCK_EXACT_MINB
+#define FLOCK_EXACT_MINB 2
+#endif
 template <typename TO, int LANES, bool EXACT, bool KNN>
-__global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? 2 : FLOCK_MINB) flock_env_kernel(const KArgs a) {
+__global__ void __launch_bounds__(FLOCK_MAXT, EXACT ? FLOCK_EXACT_MINB : FLOCK_MINB) flock_env_kernel(const KArgs a) {
     static_assert(!EXACT || (!std::is_same<TO, float>::value && LANES == 1), "EXACT is fp64, one thread per row");
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned *masks = reinterpret_cast<unsigned *>(smem + a.off_masks);

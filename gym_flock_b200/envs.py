@@ -199,7 +199,7 @@ class FlockingRelativeEnv:
         self._sync_device(for_step=True)
         self.u = u * self.action_scalar                      # :96 (attribute only; the kernel redoes it)
         eng.step(np.asarray(u, dtype=np.float64)[None])
-        self._x = eng.x[0].copy()
+        self._x[...] = eng.x[0]                              # in place, as the reference (:97-105): views such as init_vel stay live
         self._shadow = self._x.copy()
         self._pull(eng)
         return (self.state_values, self.state_network), self.instant_cost(), False, {}
@@ -407,7 +407,7 @@ class FlockingLeaderEnv(FlockingRelativeEnv):
         self._sync_device(for_step=True)
         self.u = u
         eng.step(np.asarray(u, dtype=np.float64)[None])
-        self._x = eng.x[0].copy()
+        self._x[...] = eng.x[0]                              # in place, as the reference (:97-105): views such as init_vel stay live
         self._shadow = self._x.copy()
         self._pull(eng)
         return (self.state_values, self.state_network), self.instant_cost(), False, {}
@@ -463,7 +463,7 @@ class FlockingObstacleEnv(FlockingRelativeEnv):
         eng = self._engine()
         self.u = u
         eng.step(np.asarray(u, dtype=np.float64)[None])
-        self._x = eng.x[0].copy()
+        self._x[...] = eng.x[0]                              # in place, as the reference (:97-105): views such as init_vel stay live
         self._shadow = self._x.copy()
         self._pull(eng)
         return (self.state_values, self.state_network), self.instant_cost(), False, {}

@@ -24,6 +24,10 @@ def test_make_reset_rollout_matches_smoke_golden():
     np.random.seed(0)
     values0, net0 = env.reset()
     assert np.allclose(env.env.x, g["x0"], rtol=0, atol=1e-12)      # libm cos/sin may differ in the last ulp
+    # step() integrates env.x in place (flocking_relative.py:97-105), so the view reset() leaves in init_vel (:188) stays live
+    x_obj, iv = env.env.x, env.env.init_vel
+    env.step(env.env.controller())
+    assert env.env.x is x_obj and np.shares_memory(iv, env.env.x) and np.array_equal(iv, env.env.x[:, 2:4])
     env.env.set_state(g["x0"])                                       # continue from the committed BYTES
     assert np.array_equal(env.env.state_values, g["values_0"]) and np.array_equal(env.env.state_network, g["adj_mean_0"])
     rewards = []
