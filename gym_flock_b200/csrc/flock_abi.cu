@@ -58,6 +58,8 @@ inline int tune_group(const FlockParams *p) { return (p->reserved >> 16) & 0xff;
 inline bool tune_no_group(const FlockParams *p) { return (p->reserved >> 24) & 1; }
 inline bool tune_no_pdl(const FlockParams *p) { return (p->reserved >> 25) & 1; }
 inline bool tune_no_fuse(const FlockParams *p) { return (p->reserved >> 26) & 1; }
+inline bool tune_no_bulk(const FlockParams *p) { return (p->reserved >> 29) & 1; }       // bit 29: exact-order fill as plain stores
+constexpr size_t kZeroBlock = 16 * 1024;
 inline bool tune_obs_staged(const FlockParams *p) { return (p->reserved >> 27) & 1; }   // bit 27: stage the kNN rows in smem
 
 struct Plan {
@@ -237,6 +239,11 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl, bool need_bits = false
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
                     N, pl.smem, kMaxSmem);
+    size_t zero_block = 0;      // exact order, zero-fill + scatter: a block of zeros for the TMA bulk fill, if two CTAs still fit an SM
+    if (pl.exact && !tune_no_bulk(p)) {
+        const size_t base = (pl.smem + 127) & ~(size_t)127;
+        if (2 * (base + kZeroBlock + 1024) <= 228 * 1024) { zero_block = kZeroBlock; k.off_zero = (unsigned)base; pl.smem = base + kZeroBlock; }
+    }
     k.E = E; k.N = N; k.RT = RT; k.tiles = tiles; k.GMAX = GMAX; k.row_lo = row_lo; k.row_hi = row_hi;
     k.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
     {
@@ -251,6 +258,8 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl, bool need_bits = false
     // sharded rows / several lanes per row: zero-fill + scatter
     // (exact-order mode with long rows keeps the up-front fill: its long sequential compute phase hides it)
     k.out_mode = (lanes == 1 && nrows == N && !(pl.exact && (size_t)N * tbytes > 2048) && !(tune_phases(p) & 16)) ? 1 : 0;
+    k.zero_bytes = (k.out_mode == 0 && lanes == 1 && nrows == N) ? (unsigned)zero_block : 0u;
+    if (k.zero_bytes == 0 && zero_block) pl.smem -= zero_block;
     k.W = W; k.NP2 = NP2; k.thrC = std::max(p->comm_radius, p->comm_radius2); k.R = p->comm_radius; k.R2 = p->comm_radius2;
     k.dt = p->dt; k.ascale = p->action_scalar; k.inv_ascale = 1.0 / p->action_scalar; k.var = step_variant(p);
     k.ulim = 10.0 * k.inv_ascale;

@@ -78,7 +78,18 @@ struct KArgs {
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
     int out_mode; // dense adjacency output: 0 = zero-fill up front + the non-zeros stored over it; 1 = in-warp row expansion
     int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
+    unsigned off_zero, zero_bytes;   // out_mode 0, exact order, full rows: a block of zeros in shared memory that the warps'
+                                     // row runs are filled from with 1-D TMA bulk stores (0: plain streaming stores)
 };
+
+// ---- 1-D TMA bulk stores shared -> global (the async proxy: the issuing warp never waits in the LSU's store queue) -------
+__device__ __forceinline__ void bulk_store(void *dst_global, const unsigned src_shared, const unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(__cvta_generic_to_global(dst_global)), "r"(src_shared), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }   // writes complete
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 constexpr int MS = FLOCK_MAXT;     // mask words are stored word-major with a fixed stride: word w of thread t at masks[w * MS + t]
 
@@ -454,6 +465,13 @@ __device__ __forceinline__ void stage_window(const KArgs &a, unsigned char *smem
 
     // ---- stats flags ----------------------------------------------------------------------------------------------------
     for (int q = tid; q < nenv; q += nthr) stats[q * STATS_PER_ENV + 2] = 0.0;
+    if constexpr (EXACT) {      // the zero block the bulk stores read (generic writes -> async-proxy reads: proxy fence)
+        if (a.zero_bytes) {
+            float4 *z = reinterpret_cast<float4 *>(smem + a.off_zero);
+            for (unsigned q = (unsigned)tid; q < a.zero_bytes / 16u; q += (unsigned)nthr) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async();
+        }
+    }
 
     // ---- prologue: load, integrate, publish x', stage (one flat loop over the agents of the staged envs) -----------
     {
@@ -605,6 +623,26 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
             float4 *d4 = reinterpret_cast<float4 *>(out + headn);
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             unsigned v = (unsigned)lane;
+            if constexpr (EXACT) {
+                // Exact order: the compute phase is long and LDS-heavy, and a warp that issues its run as STG sits in the
+                // store queue's throttle -- with it every shared-memory load of the SM (measured at 1024 x 1000: step =
+                // compute 1.09 ms + fill 1.41 ms, no overlap, wherever the stores were issued).  Bulk stores from a block
+                // of zeros leave the LSU alone; the warp waits for them only before it stores the non-zeros.
+                if (a.zero_bytes) {
+                    if (lane == 0) {
+                        char *dst = reinterpret_cast<char *>(d4);
+                        const unsigned zs = (unsigned)__cvta_generic_to_shared(smem + a.off_zero);
+                        for (size_t left = (size_t)nvec * 16u; left > 0;) {
+                            const unsigned nb = (unsigned)min(left, (size_t)a.zero_bytes);
+                            bulk_store(dst, zs, nb);
+                            dst += nb; left -= nb;
+                        }
+                        bulk_commit();
+                    }
+                    s0 = s1;
+                    continue;
+                }
+            }
             for (; v + 7u * 32u < nvec; v += 8u * 32u) {
 #pragma unroll
                 for (unsigned q = 0; q < 8u; ++q) __stcs(d4 + v + q * 32u, z4);
@@ -1042,16 +1080,36 @@ __device__ __forceinline__ void compute_rows(const KArgs &a, unsigned char *smem
         return;
     }
     // out_mode 0: store the few non-zero entries (1/deg) over the warp's zero-filled rows.  A warp only ever touches its
-    // own rows; __syncwarp orders the lanes' zero stores before the non-zero stores.
+    // own rows; __syncwarp orders the lanes' zero stores before the non-zero stores (bulk stores: lane 0 waits for their
+    // completion first; the proxy fence orders the async-proxy writes before the generic stores that follow).
+    if constexpr (EXACT) {
+        if (a.zero_bytes && lane == 0 && !(a.tune & 1)) { bulk_wait_all(); fence_proxy_async(); }
+    }
     __syncwarp();
     if (valid && !(a.tune & 2)) {
         TO *orow = net + grow * N;
         int w = 0;
         unsigned ex = nw > 0 ? mrow[0] : 0u;
+        // fp64 rows that start on a 32-byte sector (one thread per row): a non-zero is stored together with the other three
+        // entries of its sector, as ONE 32-byte store.  An 8-byte store into a row that has already left the L2 is a
+        // read-modify-write of the sector in HBM (ECC); a whole sector is just a write.
+        bool whole = false;
+        if constexpr (sizeof(TO) == 8 && LANES == 1) whole = ((reinterpret_cast<uintptr_t>(orow) & 31u) == 0u) && !(a.tune & 64);
         while (w < nw) {
             if (ex == 0) { ++w; ex = (w < nw) ? mrow[w * MS] : 0u; }
             if (ex != 0) {
                 const int k = __ffs(ex) - 1;
+                if constexpr (sizeof(TO) == 8 && LANES == 1) {
+                    const int k4 = k & ~3, j4 = w * 32 + k4;             // LANES == 1: j_of(k) = k
+                    if (whole && j4 + 4 <= N) {
+                        const unsigned q = ex >> k4;                     // (bits below k in this sector are already clear)
+                        ex &= ~(0xFu << k4);
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                                     :: "l"(orow + j4), "d"((q & 1u) ? (double)idg : 0.0), "d"((q & 2u) ? (double)idg : 0.0),
+                                        "d"((q & 4u) ? (double)idg : 0.0), "d"((q & 8u) ? (double)idg : 0.0) : "memory");
+                        continue;
+                    }
+                }
                 ex &= ex - 1;
                 orow[j_of(w * 32 + k)] = idg;
             }

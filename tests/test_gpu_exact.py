@@ -37,7 +37,7 @@ def test_exact_mode_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("e,n,cen,knn", [(37, 100, True, False), (64, 50, False, True), (5, 257, True, True),
-                                          (2, 1000, True, False), (3, 1, True, False), (9, 7, False, True)])
+                                          (2, 1000, True, False), (3, 301, False, False), (2, 300, False, True), (3, 1, True, False), (9, 7, False, True)])
 def test_exact_mode_batch_vs_oracle(e, n, cen, knn):
     """Cached-action rollouts (u=None) over a batch: every env bit-equal to the scalar C oracle."""
     from gym_flock_b200 import HostFlockBatch
