@@ -22,7 +22,10 @@ import argparse
 import hashlib
 import json
 import os
+import re
+import shutil
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -70,26 +73,52 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
-def kernel_source_sha():
-    """Hash of the CUDA sources: a DRAM-traffic figure captured under ncu only describes the kernels it was captured from."""
-    h = hashlib.sha256()
-    d = os.path.join(ROOT, "gym_flock_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".hpp")):
-            h.update(open(os.path.join(d, f), "rb").read())
-    return h.hexdigest()[:16]
+# the dominant kernel of every config (mangled, as cuobjdump lists it): the DRAM-traffic figures of profiles/traffic.json are keyed
+# to the SASS of exactly these functions
+TRAFFIC_KERNELS = {
+    "C2": "_ZN5flock18flock_group_kernelIfLb0ELi100ELi512EEEvNS_5GArgsE",
+    "C2k": "_ZN5flock18flock_group_kernelIfLb1ELi100ELi512EEEvNS_5GArgsE",
+    "C3": "_ZN5flock18flock_group_kernelIfLb0ELi50ELi256EEEvNS_5GArgsE",
+    "C4": "_ZN5flock16flock_env_kernelIdLi1ELb0ELb0EEEvNS_5KArgsE",
+    "C4x": "_ZN5flock16flock_env_kernelIdLi1ELb1ELb0EEEvNS_5KArgsE",
+    "C5": "_ZN5flock18flock_swarm_kernelIfLi32ELb1EEEvNS_5SArgsE",
+}
+_SASS_SHA = {}
+
+
+def kernel_sass_sha(name, lib_path=None):
+    """Hash of the SASS of config `name`'s dominant kernel in the built library (cuobjdump -sass -fun): a DRAM-traffic figure
+    captured under ncu describes the machine code it was captured from, nothing else.  None if it cannot be read."""
+    if lib_path is None:
+        from gym_flock_b200 import _lib
+        lib_path = _lib.LIB_PATH
+    key = (name, lib_path)
+    if key not in _SASS_SHA:
+        sha = None
+        try:
+            exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+            txt = subprocess.run([exe, "-sass", "-fun", TRAFFIC_KERNELS[name], lib_path], capture_output=True, text=True,
+                                 timeout=120).stdout
+            ins = [ln.strip() for ln in txt.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln)]
+            if ins:
+                sha = hashlib.sha256("\n".join(ins).encode()).hexdigest()[:16]
+        except Exception:
+            sha = None
+        _SASS_SHA[key] = sha
+    return _SASS_SHA[key]
 
 
 def recorded_traffic(name, steps_per_launch=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu capture recorded in profiles/traffic.json (bytes per
-    step of the captured launch x the steps one launch of THIS run makes) -- only if that capture was taken from the kernels of
-    this tree (source hash), else None."""
+    step of the captured launch x the steps one launch of THIS run makes) -- only if the kernel of the loaded library is, SASS
+    instruction for instruction, the kernel that capture was taken from; else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)
-        if t.get("src_sha") != kernel_source_sha():
+            t = json.load(f)[name]
+        sha = kernel_sass_sha(name)
+        if sha is None or t.get("sass_sha") != sha:
             return None
-        return float(t[name]["bytes_per_step"]) * steps_per_launch
+        return float(t["bytes_per_step"]) * steps_per_launch
     except Exception:
         return None
 

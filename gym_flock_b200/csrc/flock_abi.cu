@@ -239,10 +239,13 @@ int make_plan(const FlockParams *p, int tbytes, Plan &pl, bool need_bits = false
     if (pl.smem > kMaxSmem)
         return fail(FLOCK_EUNSUPPORTED, "N=%d needs %zu B of shared memory per CTA (> %zu): beyond the env-resident kernel",
                     N, pl.smem, kMaxSmem);
-    size_t zero_block = 0;      // exact order, zero-fill + scatter: a block of zeros for the TMA bulk fill, if two CTAs still fit an SM
+    size_t zero_block = 0;      // exact order, zero-fill + scatter: a block of zeros for the TMA bulk fill, unless it costs a resident CTA
     if (pl.exact && !tune_no_bulk(p)) {
         const size_t base = (pl.smem + 127) & ~(size_t)127;
-        if (2 * (base + kZeroBlock + 1024) <= 228 * 1024) { zero_block = kZeroBlock; k.off_zero = (unsigned)base; pl.smem = base + kZeroBlock; }
+        auto ctas = [](size_t smem) { return std::min<size_t>(2, (228 * 1024) / (smem + 1024)); };    // (registers allow two)
+        if (base + kZeroBlock <= kMaxSmem && ctas(base + kZeroBlock) == ctas(base)) {
+            zero_block = kZeroBlock; k.off_zero = (unsigned)base; pl.smem = base + kZeroBlock;
+        }
     }
     k.E = E; k.N = N; k.RT = RT; k.tiles = tiles; k.GMAX = GMAX; k.row_lo = row_lo; k.row_hi = row_hi;
     k.centralized = (p->flags & FLOCK_CENTRALIZED) ? 1 : 0;
