@@ -37,3 +37,19 @@ def test_reference_arm_other_ranks_exit_quietly():
     lines = _run(["--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"], {"RANK": "1", "WORLD_SIZE": "2",
                                                                                           "LOCAL_RANK": "1"})
     assert lines == []
+
+
+def test_traffic_figures_are_keyed_to_the_kernels_sass():
+    """profiles/traffic.json: every config names the SASS hash of the kernel its capture was taken from, and bench.py reports a
+    traffic figure only for a matching kernel in the built library (a rebuilt, different kernel reads as None, not as stale)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    for cfg, mangled in bench.TRAFFIC_KERNELS.items():
+        assert cfg in t and len(t[cfg]["sass_sha"]) == 16 and t[cfg]["bytes_per_step"] > 0
+        sha = bench.kernel_sass_sha(cfg)                 # cuobjdump on the in-tree library (built by build(); no GPU needed)
+        assert sha is not None and len(sha) == 16, (cfg, mangled)
+        got = bench.recorded_traffic(cfg, 20)
+        assert got == (t[cfg]["bytes_per_step"] * 20 if sha == t[cfg]["sass_sha"] else None)
+    assert bench.kernel_sass_sha("C2", lib_path="/nonexistent.so") is None
