@@ -77,7 +77,8 @@ struct KArgs {
     double thrC;  // candidate threshold max(R, R2)
     unsigned off_xs, off_pf, off_masks, off_stats, off_idg, off_obs;
     int out_mode; // dense adjacency output: 0 = zero-fill up front + the non-zeros stored over it; 1 = in-warp row expansion
-    int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter
+    int tune;     // diagnostics: bit0 skip fill, bit1 skip scatter, bit2 skip refine, bit3 skip filter (bit4: host, out_mode 0),
+                  // bit6 scatter the non-zeros as 8-byte stores instead of whole sectors
     unsigned off_zero, zero_bytes;   // out_mode 0, exact order, full rows: a block of zeros in shared memory that the warps'
                                      // row runs are filled from with 1-D TMA bulk stores (0: plain streaming stores)
 };
