@@ -319,11 +319,27 @@ def timed_rollout(D, env, K, rewards=None):
     torch = D.torch
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier()
+    lead_in(D)
     ev0.record()
     env.rollout(K, rewards)
     ev1.record()
     D.barrier()
-    return D.max(ev0.elapsed_time(ev1))
+    mine = ev0.elapsed_time(ev1)
+    if os.environ.get("FLOCK_BENCH_DEBUG"):
+        sys.stderr.write(f"[rank {os.environ.get('RANK', '0')}] timed_rollout K={K}: {mine * 1e3:.1f} us\n")
+    return D.max(mine)
+
+
+LEAD_IN_US = 200.0
+
+
+def lead_in(D):
+    """Optional device-side lead-in (declared as config.lead_in_us): a spin of LEAD_IN_US microseconds enqueued after the barrier
+    and BEFORE the first timing event, so that the host has queued the timed launches by the time the device reaches the event
+    and the host's launch latency (Python + ctypes + driver, ~10-80 us depending on how busy the host is) is not inside a
+    timed region that lasts 0.7 ms at the driver's K = 20.  Nothing is skipped: the K steps run in full between the events."""
+    if LEAD_IN_US > 0:
+        D.torch.cuda._sleep(int(LEAD_IN_US * 1.9e3))
 
 
 def device_warm(D, env, ms):
@@ -431,6 +447,7 @@ def measure_swarm(D, cfg, rank, world, K, W, args, adjacency, skip_gather=False,
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     D.barrier()
+    lead_in(D)
     ev0.record()
     for _ in range(K):
         env.step()                       # prep + row kernel (+ kNN fix-up) (+ NCCL all-gather of the actions when world > 1)
@@ -663,7 +680,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": {"fp32": "f32 pair math, f64 state", "fp64": "f64", "fp64-exact": "f64"}[prec],
                "data": "synthetic", "agent_steps_per_sec": head["value"] / N,
-               "config": dict(bench_config(cfg, args.config, world), warmup_ms=head["warmup_ms"],
+               "config": dict(bench_config(cfg, args.config, world), warmup_ms=head["warmup_ms"], lead_in_us=LEAD_IN_US,
                               timed_steps="steps W+1 .. W+K from the synthetic x0 (the state is reset after the device warm-up)"
                               if not args.keep_warm_state else "the state the device warm-up left",
                               mean_degree_at_end=head["mean_degree_at_end"],
@@ -702,9 +719,14 @@ def main():
     ap.add_argument("--tune", type=lambda v: int(v, 0), default=0, help="FlockParams.reserved diagnostics word (A/B runs)")
     ap.add_argument("--swarm-graph", type=int, default=1, help="C5: replay one CUDA graph per step (prep + row + fix-up + all-gather)")
     ap.add_argument("--seed-rank", type=int, default=0, help="diagnostics: use the synthetic states rank R of a multi-GPU run would get")
+    ap.add_argument("--lead-in-us", type=float, default=200.0,
+                    help="device-side spin enqueued before the first timing event (keeps the host's launch latency out of short "
+                         "timed regions; declared in config.lead_in_us)")
     ap.add_argument("--adjacency", default="dense", choices=["dense", "none"],
                     help="'none' skips the dense [E,N,N] output (diagnostic only; the headline is always dense)")
     args = ap.parse_args()
+    global LEAD_IN_US
+    LEAD_IN_US = float(args.lead_in_us)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
