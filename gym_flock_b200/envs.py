@@ -412,6 +412,18 @@ class FlockingLeaderEnv(FlockingRelativeEnv):
         self._pull(eng)
         return (self.state_values, self.state_network), self.instant_cost(), False, {}
 
+    def render(self, mode='human'):
+        """flocking_leader.py:42-57: the base scatter plus one red arrow per leader (position, velocity)."""
+        super().render(mode)
+        lead = self._x[:self.n_leaders]
+        if self.quiver is None:
+            self.quiver = self.ax.quiver(lead[:, 0], lead[:, 1], lead[:, 2], lead[:, 3], color='r')
+        else:
+            self.quiver.set_offsets(lead[:, 0:2])
+            self.quiver.set_UVC(lead[:, 2], lead[:, 3])
+        self.fig.canvas.draw()
+        self.fig.canvas.flush_events()
+
     def _set_leader_velocity(self, vel):
         """The in-place edit of flocking_leader.py:38-39.  The reference does NOT recompute its helpers afterwards, so the
         features it returns and the first controller() call still describe the state before the edit; step() then
@@ -447,6 +459,17 @@ class FlockingObstacleEnv(FlockingRelativeEnv):
 
     def _variant(self) -> dict:
         return dict(step_scale=1.0, n_obstacles=int(self.n_obstacles))
+
+    def render(self, mode='human'):
+        """flocking_obstacle.py:106-118: the base scatter with the obstacles drawn over it in red."""
+        super().render(mode)
+        obst = self._x[:self.n_obstacles]
+        if self.line2 is None:
+            self.line2, = self.ax.plot(obst[:, 0], obst[:, 1], 'ro')
+        self.line2.set_xdata(obst[:, 0])
+        self.line2.set_ydata(obst[:, 1])
+        self.fig.canvas.draw()
+        self.fig.canvas.flush_events()
 
     def _engine(self):
         # the engine is rebuilt when the number of obstacles changes (it is a launch parameter)

@@ -121,3 +121,52 @@ def test_drop_in_surface_and_synthetic_states():
     d = a[:, None, :2] - a[None, :, :2]
     r2 = (d ** 2).sum(-1) + np.eye(50) * 9
     assert r2.min() >= 0.01
+
+
+def test_render_overlays_of_the_leader_and_obstacle_envs(monkeypatch):
+    """render() is a matplotlib pass-through (flocking_relative.py:234-257); the leader env adds an arrow per leader
+    (flocking_leader.py:42-57), the obstacle env draws its obstacles over the scatter (flocking_obstacle.py:106-118).
+    Host-only: a recording stand-in for matplotlib, no device."""
+    import sys
+    import types
+    import numpy as np
+    calls = []
+
+    class Rec:
+        def __init__(self, name): self.name = name
+        def __getattr__(self, attr):
+            def f(*a, **k):
+                calls.append((self.name, attr, a))
+                if attr in ("plot",):
+                    return (Rec("line"),)
+                return Rec(attr)
+            return f
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    ax = Rec("ax")
+    fig = Rec("fig")
+    fig.canvas = Rec("canvas")
+    fig.add_subplot = lambda *a: ax
+    plt.ion = lambda: None
+    plt.figure = lambda: fig
+    plt.ylim = plt.xlim = plt.title = lambda *a, **k: None
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    from gym_flock_b200.envs import FlockingLeaderEnv, FlockingObstacleEnv
+    rng = np.random.default_rng(0)
+    lead = FlockingLeaderEnv()
+    lead._x = rng.standard_normal((lead.n_agents, 4))
+    lead.render()
+    q = [c for c in calls if c[1] == "quiver"]
+    assert len(q) == 1 and np.array_equal(q[0][2][0], lead._x[:2, 0]) and np.array_equal(q[0][2][3], lead._x[:2, 3])
+    lead.render()                                            # second frame: the arrows are moved, not re-created
+    assert len([c for c in calls if c[1] == "quiver"]) == 1
+    assert any(c[1] == "set_UVC" for c in calls) and any(c[1] == "set_offsets" for c in calls)
+    calls.clear()
+    obst = FlockingObstacleEnv()
+    obst._x = rng.standard_normal((obst.n_agents, 4))
+    obst.render()
+    red = [c for c in calls if c[1] == "plot" and len(c[2]) == 3 and c[2][2] == 'ro']
+    assert len(red) == 1 and np.array_equal(red[0][2][0], obst._x[:4, 0])
